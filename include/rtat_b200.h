@@ -1,0 +1,127 @@
+/*
+ * rtat_b200.h — C ABI of the B200-native BLAS back end for rtatblas' GEMM execution path.
+ *
+ * This is the drop-in boundary.  The reference reaches the GPU only through the `rtat::gpu::`
+ * alias table (reference src/gpu-api/gpu-api.h:87-113), which forwards to cuBLAS-v2 entry points.
+ * Every function below replaces exactly one of those aliases and keeps the cuBLAS-v2 calling
+ * convention: column-major storage, `int` dimensions, alpha/beta passed as HOST pointers, all work
+ * enqueued asynchronously on the stream bound to the handle, an integer status returned
+ * (0 == success; numbering follows cublasStatus_t so existing `== BLAS_STATUS_SUCCESS` checks hold).
+ *
+ *   reference alias (gpu-api.h line)          replacement
+ *   ---------------------------------------   -------------------------------
+ *   gpu::blasCreate        (:91)              rtat_b200_create
+ *   gpu::blasDestroy       (:92)              rtat_b200_destroy
+ *   gpu::blasSetStream     (:102)             rtat_b200_set_stream
+ *   gpu::blasGetStream     (:101)             rtat_b200_get_stream
+ *   gpu::blasDgemm         (:94)              rtat_b200_dgemm
+ *   gpu::blasSgemm         (:98)              rtat_b200_sgemm
+ *   gpu::blasDgeam         (:93)              rtat_b200_dgeam
+ *   gpu::blasSgeam         (:97)              rtat_b200_sgeam
+ *   gpu::randGenerateUniform[Double] (:119-120)  rtat_b200_fill_uniform_{s,d}   (seeded; drivers only)
+ *
+ * There is no CPU fallback and no vendor-BLAS call behind these functions: they launch hand-written
+ * sm_100a kernels or fail with a non-zero status.
+ *
+ * No torch / C++ types cross this boundary: plain pointers and sizes only.  `stream` arguments are
+ * `cudaStream_t` values passed as `void*` so that the header has no CUDA include dependency.
+ */
+#ifndef RTAT_B200_H
+#define RTAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTAT_B200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes (cublasStatus_t numbering) -------------------------------------------------- */
+enum {
+  RTAT_B200_STATUS_SUCCESS = 0,
+  RTAT_B200_STATUS_NOT_INITIALIZED = 1,
+  RTAT_B200_STATUS_ALLOC_FAILED = 3,
+  RTAT_B200_STATUS_INVALID_VALUE = 7,
+  RTAT_B200_STATUS_ARCH_MISMATCH = 8,
+  RTAT_B200_STATUS_EXECUTION_FAILED = 13,
+  RTAT_B200_STATUS_INTERNAL_ERROR = 14,
+  RTAT_B200_STATUS_NOT_SUPPORTED = 15
+};
+
+/* ---- operation flags (cublasOperation_t numbering; reference gpu-api.h:112-113) --------------- */
+enum { RTAT_B200_OP_N = 0, RTAT_B200_OP_T = 1 };
+
+typedef struct rtat_b200_context *rtat_b200_handle_t;
+
+int rtat_b200_version(void);
+const char *rtat_b200_status_string(int status);
+
+/* ---- handle management (replaces cublasCreate/Destroy/SetStream/GetStream) --------------------- */
+int rtat_b200_create(rtat_b200_handle_t *handle);
+int rtat_b200_destroy(rtat_b200_handle_t handle);
+int rtat_b200_set_stream(rtat_b200_handle_t handle, void *stream /* cudaStream_t */);
+int rtat_b200_get_stream(rtat_b200_handle_t handle, void **stream /* cudaStream_t* */);
+
+/* ---- GEMM:  C = alpha * op(A) * op(B) + beta * C   (replaces cublasDgemm / cublasSgemm) --------
+ * op(A) is m x k, op(B) is k x n, C is m x n, all column-major with leading dimensions lda/ldb/ldc.
+ * beta == 0 means C is write-only (never read, so NaN/uninitialised scratch is fine — the
+ * reference hands uninitialised scratch as C: matrixop.h:433-436).
+ * dgemm runs FP64 DMMA tiles.  sgemm is FP32-faithful: 3xTF32 split products on tcgen05 tensor
+ * cores with FP32 accumulation, or an FP32 FMA kernel for operands TMA cannot address. */
+int rtat_b200_dgemm(rtat_b200_handle_t handle, int transa, int transb, int m, int n, int k,
+                    const double *alpha, const double *A, int lda, const double *B, int ldb,
+                    const double *beta, double *C, int ldc);
+int rtat_b200_sgemm(rtat_b200_handle_t handle, int transa, int transb, int m, int n, int k,
+                    const float *alpha, const float *A, int lda, const float *B, int ldb,
+                    const float *beta, float *C, int ldc);
+
+/* ---- GEAM:  C = alpha * op(A) + beta * op(B)   (replaces cublasDgeam / cublasSgeam) ------------
+ * C is m x n.  The reference always calls this with transb == N and C aliasing B (in place,
+ * ldb == ldc; matrixop.h:302,340-341); that aliasing is supported.  C aliasing A is supported only
+ * for transa == N with lda == ldc.  beta == 0 means B is never read; alpha == 0 means A is never
+ * read.  Results are bit-identical to cuBLAS geam: one rounding of alpha*a, one of beta*b, one of
+ * the sum (no FMA contraction) — verified against the reference executor, see tests/golden. */
+int rtat_b200_dgeam(rtat_b200_handle_t handle, int transa, int transb, int m, int n,
+                    const double *alpha, const double *A, int lda, const double *beta,
+                    const double *B, int ldb, double *C, int ldc);
+int rtat_b200_sgeam(rtat_b200_handle_t handle, int transa, int transb, int m, int n,
+                    const float *alpha, const float *A, int lda, const float *beta, const float *B,
+                    int ldb, float *C, int ldc);
+
+/* ---- seeded uniform fill in (lo, hi]  (replaces the unseeded cuRAND fill of the drivers) -------
+ * Counter-based (SplitMix64 of seed + element index): the same (seed, index) gives the same value
+ * on any grid, so hosts can regenerate inputs without copying them. */
+int rtat_b200_fill_uniform_d(rtat_b200_handle_t handle, double *x, size_t n, uint64_t seed,
+                             double lo, double hi);
+int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint64_t seed, float lo,
+                             float hi);
+
+/* ---- tuning / introspection (no reference counterpart) ------------------------------------------
+ * rtat_b200_set_option:  "dgemm.variant", "sgemm.variant", "geam.variant" select a kernel family
+ *   explicitly (0 = automatic).  Used by the tests to force every code path and by the planner's
+ *   fused/explicit plan dimension.
+ * rtat_b200_last_kernel: name of the kernel variant the most recent call on this handle launched.
+ * rtat_b200_launch_count: number of kernel launches issued through this handle so far. */
+int rtat_b200_set_option(rtat_b200_handle_t handle, const char *key, int value);
+int rtat_b200_get_option(rtat_b200_handle_t handle, const char *key, int *value);
+const char *rtat_b200_last_kernel(rtat_b200_handle_t handle);
+uint64_t rtat_b200_launch_count(rtat_b200_handle_t handle);
+
+/* ---- host-buffer entry points ---------------------------------------------------------------------
+ * Same contract as dgemm/sgemm but A, B, C are HOST pointers (pinned or pageable).  Operands are
+ * staged through the handle's device arena (grown on demand), the GEMM runs on the handle's stream,
+ * and C is copied back; the call returns after C is valid on the host.  This is what a caller that
+ * keeps its matrices in host memory sees, and what bench.py times as the end-to-end number. */
+int rtat_b200_dgemm_host(rtat_b200_handle_t handle, int transa, int transb, int m, int n, int k,
+                         const double *alpha, const double *A, int lda, const double *B, int ldb,
+                         const double *beta, double *C, int ldc);
+int rtat_b200_sgemm_host(rtat_b200_handle_t handle, int transa, int transb, int m, int n, int k,
+                         const float *alpha, const float *A, int lda, const float *B, int ldb,
+                         const float *beta, float *C, int ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTAT_B200_H */

@@ -1,0 +1,70 @@
+"""Quick kernel timing through the C ABI (not the bench contract; development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rtatblas_b200 as rt
+
+h = rt.Handle(stream=torch.cuda.current_stream())
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def dgemm_cfg(name, ta, tb, m, n, k, variants=(1, 2), dtype=torch.float64, opts=()):
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    A = torch.empty(ar * ac, dtype=dtype, device="cuda"); h.fill_uniform(A, 1)
+    B = torch.empty(br * bc, dtype=dtype, device="cuda"); h.fill_uniform(B, 2)
+    Cm = torch.empty(m * n, dtype=dtype, device="cuda")
+    dbl = dtype == torch.float64
+    key = "dgemm.variant" if dbl else "sgemm.variant"
+    for v in variants:
+        h.set_option(key, v)
+        for k_, v_ in opts: h.set_option(k_, v_)
+        try:
+            ms = timeit(lambda: h.gemm(dbl, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m))
+            print(f"{name:34s} variant {v} {h.last_kernel():36s} {ms:9.3f} ms {2.0*m*n*k/ms*1e-9:8.2f} TFLOP/s", flush=True)
+        except rt.RtatError as e:
+            print(f"{name:34s} variant {v} unsupported: {e}")
+        h.set_option(key, 0)
+
+
+def geam_cfg(name, ta, m, n, ldc=None, dtype=torch.float64):
+    ar, ac = (n, m) if ta else (m, n)
+    ldc = ldc or m
+    A = torch.empty(ar * ac, dtype=dtype, device="cuda"); h.fill_uniform(A, 1)
+    Cm = torch.empty(ldc * n, dtype=dtype, device="cuda")
+    ms = timeit(lambda: h.geam(dtype == torch.float64, ta, 0, m, n, 1.0, A, ar, 0.0, Cm, ldc, Cm, ldc))
+    print(f"{name:34s} {h.last_kernel():30s} {ms:9.4f} ms {2.0*m*n*A.element_size()/ms*1e-6:8.1f} GB/s", flush=True)
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "dgemm"):
+    dgemm_cfg("C1 dgemm NN 1024^3", 0, 0, 1024, 1024, 1024)
+    dgemm_cfg("C2 dgemm TN 8192^3", 1, 0, 8192, 8192, 8192, variants=(1,))
+    dgemm_cfg("C2' dgemm NN 8192^3", 0, 0, 8192, 8192, 8192, variants=(1,))
+    dgemm_cfg("C2'' dgemm NT 8192^3", 0, 1, 8192, 8192, 8192, variants=(1,))
+    dgemm_cfg("C2''' dgemm TT 8192^3", 1, 1, 8192, 8192, 8192, variants=(1,))
+    dgemm_cfg("C3 dgemm NT 4097x3001x2049", 0, 1, 4097, 3001, 2049)
+    dgemm_cfg("dgemm NN 4096^3", 0, 0, 4096, 4096, 4096)
+    dgemm_cfg("dgemm NN 2048^3", 0, 0, 2048, 2048, 2048)
+    dgemm_cfg("C5/8-like NN 8192x1024x8192", 0, 0, 8192, 1024, 8192)
+if which in ("all", "geam"):
+    geam_cfg("transpose 8192^2 f64", 1, 8192, 8192)
+    geam_cfg("copy 8192^2 f64", 0, 8192, 8192)
+    geam_cfg("pad-copy 4097x2049 ->ld4128", 0, 4097, 2049, 4128)
+    geam_cfg("transpose 4097x2049 ->ld2080", 1, 2049, 4097, 2080)
+    geam_cfg("pad-copy 3001x2049 ->ld3008", 0, 3001, 2049, 3008)
+    geam_cfg("transpose 131072x128 f32", 1, 128, 131072, dtype=torch.float32)
+if which in ("all", "sgemm"):
+    dgemm_cfg("C4 sgemm NN 131072x128x4096", 0, 0, 131072, 128, 4096, variants=(1, 2), dtype=torch.float32)
+    dgemm_cfg("sgemm NN 4096^3", 0, 0, 4096, 4096, 4096, variants=(1, 2), dtype=torch.float32)

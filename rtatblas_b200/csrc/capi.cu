@@ -1,0 +1,274 @@
+// C ABI entry points (include/rtat_b200.h): handle management, argument validation, dispatch.
+// Replaces the cuBLAS side of the reference's rtat::gpu:: alias table (src/gpu-api/gpu-api.h:87-113).
+#include "common.cuh"
+#include <cstring>
+#include <new>
+
+using namespace rtat_b200;
+
+namespace rtat_b200 {
+int ensure_arena(rtat_b200_context *h, size_t bytes) {
+  if (bytes <= h->arena_bytes) return RTAT_B200_STATUS_SUCCESS;
+  if (h->arena) {
+    // the arena may still be in use by work queued on the handle's stream
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->arena);
+    h->arena = nullptr;
+    h->arena_bytes = 0;
+  }
+  size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+  if (cudaMalloc(&h->arena, want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  h->arena_bytes = want;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+}  // namespace rtat_b200
+
+extern "C" {
+
+int rtat_b200_version(void) { return RTAT_B200_VERSION; }
+
+const char *rtat_b200_status_string(int s) {
+  switch (s) {
+    case RTAT_B200_STATUS_SUCCESS: return "RTAT_B200_STATUS_SUCCESS";
+    case RTAT_B200_STATUS_NOT_INITIALIZED: return "RTAT_B200_STATUS_NOT_INITIALIZED";
+    case RTAT_B200_STATUS_ALLOC_FAILED: return "RTAT_B200_STATUS_ALLOC_FAILED";
+    case RTAT_B200_STATUS_INVALID_VALUE: return "RTAT_B200_STATUS_INVALID_VALUE";
+    case RTAT_B200_STATUS_ARCH_MISMATCH: return "RTAT_B200_STATUS_ARCH_MISMATCH";
+    case RTAT_B200_STATUS_EXECUTION_FAILED: return "RTAT_B200_STATUS_EXECUTION_FAILED";
+    case RTAT_B200_STATUS_INTERNAL_ERROR: return "RTAT_B200_STATUS_INTERNAL_ERROR";
+    case RTAT_B200_STATUS_NOT_SUPPORTED: return "RTAT_B200_STATUS_NOT_SUPPORTED";
+    default: return "RTAT_B200_STATUS_UNKNOWN";
+  }
+}
+
+int rtat_b200_create(rtat_b200_handle_t *handle) {
+  if (!handle) return RTAT_B200_STATUS_INVALID_VALUE;
+  *handle = nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_NOT_INITIALIZED;  // no usable GPU: there is no CPU fallback
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_NOT_INITIALIZED;
+  }
+  if (prop.major != 10) {
+    fprintf(stderr, "rtat_b200: device %d is sm_%d%d; this library only contains sm_100a code\n", dev,
+            prop.major, prop.minor);
+    return RTAT_B200_STATUS_ARCH_MISMATCH;
+  }
+  auto *h = new (std::nothrow) rtat_b200_context();
+  if (!h) return RTAT_B200_STATUS_ALLOC_FAILED;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  h->stream = nullptr;  // legacy default stream until set_stream, as with cuBLAS
+  *handle = h;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_destroy(rtat_b200_handle_t h) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  cudaStreamSynchronize(h->stream);
+  if (h->arena) cudaFree(h->arena);
+  if (h->staging) cudaFree(h->staging);
+  if (h->staging_done) cudaEventDestroy(h->staging_done);
+  delete h;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_set_stream(rtat_b200_handle_t h, void *stream) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  h->stream = static_cast<cudaStream_t>(stream);
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_get_stream(rtat_b200_handle_t h, void **stream) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!stream) return RTAT_B200_STATUS_INVALID_VALUE;
+  *stream = static_cast<void *>(h->stream);
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_set_option(rtat_b200_handle_t h, const char *key, int value) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!key) return RTAT_B200_STATUS_INVALID_VALUE;
+  h->options[key] = value;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_get_option(rtat_b200_handle_t h, const char *key, int *value) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!key || !value) return RTAT_B200_STATUS_INVALID_VALUE;
+  *value = opt(h, key, 0);
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+const char *rtat_b200_last_kernel(rtat_b200_handle_t h) { return h ? h->last_kernel : "none"; }
+uint64_t rtat_b200_launch_count(rtat_b200_handle_t h) { return h ? h->launches : 0; }
+
+// ---- argument validation shared by gemm entry points (cuBLAS rules) ---------------------------
+static int validate_gemm(int transa, int transb, int m, int n, int k, int lda, int ldb, int ldc) {
+  if ((transa != RTAT_B200_OP_N && transa != RTAT_B200_OP_T) ||
+      (transb != RTAT_B200_OP_N && transb != RTAT_B200_OP_T))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  if (m < 0 || n < 0 || k < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  int rows_a = transa == RTAT_B200_OP_N ? m : k;
+  int rows_b = transb == RTAT_B200_OP_N ? k : n;
+  if (lda < (rows_a > 1 ? rows_a : 1) || ldb < (rows_b > 1 ? rows_b : 1) || ldc < (m > 1 ? m : 1))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_dgemm(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
+                    const double *alpha, const double *A, int lda, const double *B, int ldb,
+                    const double *beta, double *C, int ldc) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_gemm(transa, transb, m, n, k, lda, ldb, ldc);
+  if (st) return st;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!C || (k > 0 && *alpha != 0.0 && (!A || !B))) return RTAT_B200_STATUS_INVALID_VALUE;
+  return dgemm(h, transa, transb, m, n, k, *alpha, A, lda, B, ldb, *beta, C, ldc);
+}
+
+int rtat_b200_sgemm(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
+                    const float *alpha, const float *A, int lda, const float *B, int ldb,
+                    const float *beta, float *C, int ldc) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_gemm(transa, transb, m, n, k, lda, ldb, ldc);
+  if (st) return st;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!C || (k > 0 && *alpha != 0.f && (!A || !B))) return RTAT_B200_STATUS_INVALID_VALUE;
+  return sgemm(h, transa, transb, m, n, k, *alpha, A, lda, B, ldb, *beta, C, ldc);
+}
+
+}  // extern "C"
+
+template <typename T>
+static int geam_entry(rtat_b200_handle_t h, int transa, int transb, int m, int n, const T *alpha,
+                      const T *A, int lda, const T *beta, const T *B, int ldb, T *C, int ldc) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  if ((transa != RTAT_B200_OP_N && transa != RTAT_B200_OP_T) ||
+      (transb != RTAT_B200_OP_N && transb != RTAT_B200_OP_T))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  if (m < 0 || n < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  int rows_a = transa == RTAT_B200_OP_N ? m : n;
+  int rows_b = transb == RTAT_B200_OP_N ? m : n;
+  if (lda < (rows_a > 1 ? rows_a : 1) || ldb < (rows_b > 1 ? rows_b : 1) || ldc < (m > 1 ? m : 1))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!C) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (*alpha != T(0) && !A) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (*beta != T(0) && !B) return RTAT_B200_STATUS_INVALID_VALUE;
+  // in-place rules (cuBLAS geam): C may alias an operand only if that operand is not transposed
+  // and shares C's leading dimension
+  if (*alpha != T(0) && (const T *)C == A && (transa != RTAT_B200_OP_N || lda != ldc))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  if (*beta != T(0) && (const T *)C == B && (transb != RTAT_B200_OP_N || ldb != ldc))
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  return geam<T>(h, transa, transb, m, n, *alpha, A, lda, *beta, B, ldb, C, ldc);
+}
+
+extern "C" {
+
+int rtat_b200_dgeam(rtat_b200_handle_t h, int transa, int transb, int m, int n, const double *alpha,
+                    const double *A, int lda, const double *beta, const double *B, int ldb,
+                    double *C, int ldc) {
+  return geam_entry<double>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+}
+
+int rtat_b200_sgeam(rtat_b200_handle_t h, int transa, int transb, int m, int n, const float *alpha,
+                    const float *A, int lda, const float *beta, const float *B, int ldb, float *C,
+                    int ldc) {
+  return geam_entry<float>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+}
+
+int rtat_b200_fill_uniform_d(rtat_b200_handle_t h, double *x, size_t n, uint64_t seed, double lo,
+                             double hi) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!x) return RTAT_B200_STATUS_INVALID_VALUE;
+  return fill_uniform<double>(h, x, n, seed, lo, hi);
+}
+
+int rtat_b200_fill_uniform_s(rtat_b200_handle_t h, float *x, size_t n, uint64_t seed, float lo,
+                             float hi) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!x) return RTAT_B200_STATUS_INVALID_VALUE;
+  return fill_uniform<float>(h, x, n, seed, lo, hi);
+}
+
+}  // extern "C"
+
+// ---- host-buffer entry points ------------------------------------------------------------------
+template <typename T, typename GemmFn>
+static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
+                     const T *alpha, const T *A, int lda, const T *B, int ldb, const T *beta, T *C,
+                     int ldc, GemmFn gemm_fn) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_gemm(transa, transb, m, n, k, lda, ldb, ldc);
+  if (st) return st;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!A || !B || !C) return RTAT_B200_STATUS_INVALID_VALUE;
+  size_t cols_a = transa == RTAT_B200_OP_N ? k : m, cols_b = transb == RTAT_B200_OP_N ? n : k;
+  auto round = [](size_t b) { return (b + 511) & ~size_t(511); };
+  size_t bytes_a = round(sizeof(T) * lda * cols_a), bytes_b = round(sizeof(T) * ldb * cols_b),
+         bytes_c = round(sizeof(T) * size_t(ldc) * n);
+  size_t need = bytes_a + bytes_b + bytes_c;
+  if (need > h->staging_bytes) {
+    cudaStreamSynchronize(h->stream);
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    if (cudaMalloc(&h->staging, need) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_ALLOC_FAILED;
+    }
+    h->staging_bytes = need;
+  }
+  char *base = static_cast<char *>(h->staging);
+  T *dA = reinterpret_cast<T *>(base), *dB = reinterpret_cast<T *>(base + bytes_a),
+    *dC = reinterpret_cast<T *>(base + bytes_a + bytes_b);
+  cudaStream_t s = h->stream;
+  if (cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(dB, B, sizeof(T) * ldb * cols_b, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  if (*beta != T(0) &&
+      cudaMemcpyAsync(dC, C, sizeof(T) * size_t(ldc) * n, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  st = gemm_fn(h, transa, transb, m, n, k, *alpha, dA, lda, dB, ldb, *beta, dC, ldc);
+  if (st) return st;
+  // copy back only the m x n window (ldc padding rows on the host are left untouched)
+  if (cudaMemcpy2DAsync(C, sizeof(T) * ldc, dC, sizeof(T) * ldc, sizeof(T) * m, n,
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return RTAT_B200_STATUS_EXECUTION_FAILED;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+extern "C" {
+
+int rtat_b200_dgemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
+                         const double *alpha, const double *A, int lda, const double *B, int ldb,
+                         const double *beta, double *C, int ldc) {
+  return gemm_host<double>(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dgemm);
+}
+
+int rtat_b200_sgemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
+                         const float *alpha, const float *A, int lda, const float *B, int ldb,
+                         const float *beta, float *C, int ldc) {
+  return gemm_host<float>(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, sgemm);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Internal declarations shared by the kernels behind the C ABI (include/rtat_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <map>
+#include "../../include/rtat_b200.h"
+
+struct rtat_b200_context {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  // library-owned device arena: stream-K partial tiles, pre-split operands, host-entry staging
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
+  // tuning knobs (rtat_b200_set_option)
+  std::map<std::string, int> options;
+  // introspection
+  const char *last_kernel = "none";
+  uint64_t launches = 0;
+  // host-entry staging
+  void *staging = nullptr;
+  size_t staging_bytes = 0;
+  cudaEvent_t staging_done = nullptr;
+};
+
+namespace rtat_b200 {
+
+inline int opt(const rtat_b200_context *h, const char *key, int dflt = 0) {
+  auto it = h->options.find(key);
+  return it == h->options.end() ? dflt : it->second;
+}
+
+inline int check_launch(rtat_b200_context *h, const char *kernel, int nlaunch = 1) {
+  cudaError_t e = cudaPeekAtLastError();
+  h->last_kernel = kernel;
+  h->launches += nlaunch;
+  if (e != cudaSuccess) {
+    fprintf(stderr, "rtat_b200: launch of %s failed: %s\n", kernel, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  }
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+// grow-only device arena owned by the handle (contents are scratch; never preserved across calls)
+int ensure_arena(rtat_b200_context *h, size_t bytes);
+
+// kernel families (each defined in its own .cu)
+template <typename T>
+int geam(rtat_b200_context *h, int transa, int transb, int m, int n, T alpha, const T *A, int lda,
+         T beta, const T *B, int ldb, T *C, int ldc);
+
+int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, double alpha,
+          const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
+int sgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
+          const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+
+template <typename T>
+int fill_uniform(rtat_b200_context *h, T *x, size_t n, uint64_t seed, T lo, T hi);
+
+}  // namespace rtat_b200

@@ -1,0 +1,257 @@
+// GEAM kernels:  C = alpha * op(A) + beta * op(B)   (column-major, m x n)
+//
+// These replace cublas{D,S}geam behind the reference's MatrixMove (transpose / pad / copy,
+// reference src/matrix_ops/matrixop.h:307-344) and MatrixAccumulate (in-place fold of a scratch
+// product into C, matrixop.h:256-305).  Both are pure HBM streaming: algorithmic traffic is one read
+// of every operand that is used and one write of C.
+//
+//   geam_stream_kernel : no operand transposed.  Each thread moves 16 B vectors (or scalars when an
+//                        operand's columns are not 16 B aligned, e.g. ld = 4097 doubles) for
+//                        several columns at once so that enough bytes are in flight per SM.
+//   geam_tile_kernel   : at least one operand transposed.  64x64 tiles are staged through padded
+//                        shared memory (odd pitch => conflict-free transposed reads); global loads
+//                        run along the operand's contiguous dimension and global stores along C's.
+//
+// Arithmetic (pinned against cuBLAS through tests/golden): beta == 0 => c = alpha*a with B never
+// read; alpha == 0 => c = beta*b with A never read; otherwise round(round(alpha*a) + round(beta*b)).
+#include "common.cuh"
+
+namespace rtat_b200 {
+
+template <typename T>
+__device__ __forceinline__ T mul_rn(T a, T b);
+template <>
+__device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T add_rn(T a, T b);
+template <>
+__device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <>
+__device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T fma_rn(T a, T b, T c);
+template <>
+__device__ __forceinline__ double fma_rn<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+template <>
+__device__ __forceinline__ float fma_rn<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// MODE: 0 = alpha*a only, 1 = beta*b only, 2 = mul,mul,add  3 = fma(alpha,a,beta*b)  4 = fma(beta,b,alpha*a)
+template <typename T, int MODE>
+__device__ __forceinline__ T axpby(T alpha, T a, T beta, T b) {
+  if (MODE == 0) return mul_rn(alpha, a);
+  if (MODE == 1) return mul_rn(beta, b);
+  if (MODE == 2) return add_rn(mul_rn(alpha, a), mul_rn(beta, b));
+  if (MODE == 3) return fma_rn(alpha, a, mul_rn(beta, b));
+  return fma_rn(beta, b, mul_rn(alpha, a));
+}
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template <>
+struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+
+// ---------------------------------------------------------------------------------------------
+// streaming kernel (no transposes).  A tile is ROWS_PER_CTA rows x COLS columns.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool VEC, int COLS>
+__global__ void __launch_bounds__(256)
+geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B,
+                   int ldb, T *C, int ldc, int row_tiles) {
+  constexpr int VN = VEC ? Vec16<T>::N : 1;
+  constexpr int ROWS = 256 * VN;
+  using V = typename Vec16<T>::type;
+  for (long long tile = blockIdx.x; tile < (long long)row_tiles * ((n + COLS - 1) / COLS); tile += gridDim.x) {
+    int rt = int(tile % row_tiles), ct = int(tile / row_tiles);
+    int i = rt * ROWS + threadIdx.x * VN;
+    int j0 = ct * COLS;
+    if (VEC) {
+      if (i >= m) continue;  // m % VN == 0 is guaranteed by the dispatcher for the vector path
+      V va[COLS], vb[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; c++) {
+        int j = j0 + c;
+        if (j < n) {
+          if (MODE != 1) va[c] = *reinterpret_cast<const V *>(A + (size_t)j * lda + i);
+          if (MODE != 0) vb[c] = *reinterpret_cast<const V *>(B + (size_t)j * ldb + i);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < COLS; c++) {
+        int j = j0 + c;
+        if (j < n) {
+          V out;
+          T *o = reinterpret_cast<T *>(&out);
+          const T *pa = reinterpret_cast<const T *>(&va[c]);
+          const T *pb = reinterpret_cast<const T *>(&vb[c]);
+#pragma unroll
+          for (int e = 0; e < VN; e++) o[e] = axpby<T, MODE>(alpha, MODE != 1 ? pa[e] : T(0), beta, MODE != 0 ? pb[e] : T(0));
+          *reinterpret_cast<V *>(C + (size_t)j * ldc + i) = out;
+        }
+      }
+    } else {
+      if (i >= m) continue;
+      T va[COLS], vb[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; c++) {
+        int j = j0 + c;
+        if (j < n) {
+          if (MODE != 1) va[c] = A[(size_t)j * lda + i];
+          if (MODE != 0) vb[c] = B[(size_t)j * ldb + i];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < COLS; c++) {
+        int j = j0 + c;
+        if (j < n) C[(size_t)j * ldc + i] = axpby<T, MODE>(alpha, MODE != 1 ? va[c] : T(0), beta, MODE != 0 ? vb[c] : T(0));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile kernel (some operand transposed).  TILE x TILE elements, 256 threads.
+// Operand X contributes x(i,j) = X[j + i*ldx] when transposed (X is n x m), X[i + j*ldx] otherwise.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool TA, bool TB, int TILE>
+__global__ void __launch_bounds__(256)
+geam_tile_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb,
+                 T *C, int ldc, int tiles_m, int tiles_n) {
+  constexpr int PITCH = TILE + 1;
+  constexpr int YS = 256 / TILE;        // thread rows per pass
+  constexpr int PER = TILE / YS;        // elements per thread
+  constexpr bool USE_A = MODE != 1, USE_B = MODE != 0;
+  __shared__ T sa[(TA && USE_A) ? TILE * PITCH : 1];
+  __shared__ T sb[(TB && USE_B) ? TILE * PITCH : 1];
+  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;  // ty in 0..YS-1
+  for (long long tile = blockIdx.x; tile < (long long)tiles_m * tiles_n; tile += gridDim.x) {
+    int i0 = int(tile % tiles_m) * TILE, j0 = int(tile / tiles_m) * TILE;
+    // stage transposed operands: global reads run along the operand's own contiguous dimension (j)
+    if (TA && USE_A) {
+      int j = j0 + tx;
+#pragma unroll 8
+      for (int r = ty; r < TILE; r += YS) {
+        int i = i0 + r;
+        if (i < m && j < n) sa[r * PITCH + tx] = A[(size_t)i * lda + j];
+      }
+    }
+    if (TB && USE_B) {
+      int j = j0 + tx;
+#pragma unroll 8
+      for (int r = ty; r < TILE; r += YS) {
+        int i = i0 + r;
+        if (i < m && j < n) sb[r * PITCH + tx] = B[(size_t)i * ldb + j];
+      }
+    }
+    if ((TA && USE_A) || (TB && USE_B)) __syncthreads();
+    {
+      int i = i0 + tx;
+      if (i < m) {
+        T va[PER], vb[PER];
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+          int jj = ty + YS * r, j = j0 + jj;
+          if (j < n) {
+            if (USE_A) va[r] = TA ? sa[tx * PITCH + jj] : A[(size_t)j * lda + i];
+            if (USE_B) vb[r] = TB ? sb[tx * PITCH + jj] : B[(size_t)j * ldb + i];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+          int j = j0 + ty + YS * r;
+          if (j < n) C[(size_t)j * ldc + i] = axpby<T, MODE>(alpha, USE_A ? va[r] : T(0), beta, USE_B ? vb[r] : T(0));
+        }
+      }
+    }
+    if ((TA && USE_A) || (TB && USE_B)) __syncthreads();
+  }
+}
+
+template <typename T, int MODE>
+static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int n, T alpha, const T *A,
+                       int lda, T beta, const T *B, int ldb, T *C, int ldc) {
+  const bool ta = transa == RTAT_B200_OP_T && MODE != 1, tb = transb == RTAT_B200_OP_T && MODE != 0;
+  cudaStream_t s = h->stream;
+  const int max_ctas = h->sm_count * 8;
+  if (!ta && !tb) {
+    constexpr int VN = Vec16<T>::N;
+    auto aligned = [&](const T *p, int ld) { return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % VN == 0); };
+    bool vec = (m % VN == 0) && aligned(C, ldc) && (MODE == 1 || aligned(A, lda)) && (MODE == 0 || aligned(B, ldb));
+    if (opt(h, "geam.variant") == 1) vec = false;
+    constexpr int COLS = 4;
+    int rows = 256 * (vec ? VN : 1);
+    int row_tiles = (m + rows - 1) / rows;
+    long long tiles = (long long)row_tiles * ((n + COLS - 1) / COLS);
+    int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+    if (vec) {
+      geam_stream_kernel<T, MODE, true, COLS><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, row_tiles);
+      return check_launch(h, "geam_stream_vec16");
+    }
+    geam_stream_kernel<T, MODE, false, COLS><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, row_tiles);
+    return check_launch(h, "geam_stream_scalar");
+  }
+  const int TL = (ta && tb) ? 32 : 64;
+  int tiles_m = (m + TL - 1) / TL, tiles_n = (n + TL - 1) / TL;
+  long long tiles = (long long)tiles_m * tiles_n;
+  int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  if (ta && !tb) {
+    geam_tile_kernel<T, MODE, true, false, 64><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tiles_m, tiles_n);
+    return check_launch(h, "geam_tile_tn");
+  } else if (!ta && tb) {
+    geam_tile_kernel<T, MODE, false, true, 64><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tiles_m, tiles_n);
+    return check_launch(h, "geam_tile_nt");
+  }
+  geam_tile_kernel<T, MODE, true, true, 32><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tiles_m, tiles_n);
+  return check_launch(h, "geam_tile_tt");
+}
+
+template <typename T>
+int geam(rtat_b200_context *h, int transa, int transb, int m, int n, T alpha, const T *A, int lda,
+         T beta, const T *B, int ldb, T *C, int ldc) {
+  if (beta == T(0)) return launch_geam<T, 0>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+  if (alpha == T(0)) return launch_geam<T, 1>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+  switch (opt(h, "geam.rounding", 2)) {
+    case 3: return launch_geam<T, 3>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+    case 4: return launch_geam<T, 4>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+    default: return launch_geam<T, 2>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
+  }
+}
+
+template int geam<double>(rtat_b200_context *, int, int, int, int, double, const double *, int, double, const double *, int, double *, int);
+template int geam<float>(rtat_b200_context *, int, int, int, int, float, const float *, int, float, const float *, int, float *, int);
+
+// ---------------------------------------------------------------------------------------------
+// seeded counter-based uniform fill (drivers / tests only)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+template <typename T>
+__global__ void fill_uniform_kernel(T *x, size_t n, uint64_t seed, T lo, T hi) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ull + i);
+    // 53 random bits -> u in (0, 1]
+    double u = (double)((r >> 11) + 1) * (1.0 / 9007199254740992.0);
+    x[i] = (T)((double)lo + ((double)hi - (double)lo) * u);
+  }
+}
+
+template <typename T>
+int fill_uniform(rtat_b200_context *h, T *x, size_t n, uint64_t seed, T lo, T hi) {
+  size_t blocks = (n + 255) / 256;
+  size_t cap = (size_t)h->sm_count * 16;
+  fill_uniform_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, h->stream>>>(x, n, seed, lo, hi);
+  return check_launch(h, "fill_uniform");
+}
+template int fill_uniform<double>(rtat_b200_context *, double *, size_t, uint64_t, double, double);
+template int fill_uniform<float>(rtat_b200_context *, float *, size_t, uint64_t, float, float);
+
+}  // namespace rtat_b200

@@ -1,0 +1,9 @@
+#!/bin/bash
+# Regenerates tests/golden/reference_b200.{bin,json}: outputs of the UNMODIFIED reference executor
+# (oracle/_ref/ref_driver = /root/reference/src compiled in place + oracle/ref_driver.cpp, cuBLAS 12.9)
+# on seeded inputs.  Needs a GPU:   gpurun -- 'bash tests/golden/make_golden.sh'
+# then copy gpurun_out/golden/* into tests/golden/.
+set -e
+mkdir -p gpurun_out/golden
+oracle/_ref/ref_driver golden gpurun_out/golden/reference_b200.bin gpurun_out/golden/reference_b200.json
+ls -la gpurun_out/golden

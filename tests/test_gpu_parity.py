@@ -1,0 +1,201 @@
+"""-m gpu parity tests: the sm_100a kernels, called through the C ABI (include/rtat_b200.h), against
+the CPU oracle on the same seeded inputs.  geam is bit-exact; gemm is held to BASELINE.json's bound.
+Shapes follow the reference's own tests (tests/executor_test.cpp, matrixop_test.cpp,
+planning_test.cpp) plus tile-boundary, ragged, unaligned and degenerate cases."""
+import numpy as np
+import pytest
+import torch
+
+import rtatblas_b200 as rt
+from gpu_util import dev, gemm_tolerance, host
+from oracle_binding import view
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm_case(oracle, handle, dtype, ta, tb, m, n, k, alpha, beta, seed, lda_pad=0, ldb_pad=0, ldc_pad=0, offset=0,
+               nan_c=False):
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    lda, ldb, ldc = max(ar, 1) + lda_pad, max(br, 1) + ldb_pad, max(m, 1) + ldc_pad
+    A = oracle.fill(lda * ac + offset, seed, dtype)
+    B = oracle.fill(ldb * bc + offset, seed + 1, dtype)
+    C0 = oracle.fill(ldc * n + offset, seed + 2, dtype)
+    if nan_c:
+        C0[:] = np.nan
+    dA, dB, dC = dev(A), dev(B), dev(C0)
+    isz = A.itemsize
+    handle.gemm(dtype == np.float64, int(ta), int(tb), m, n, k, alpha, dA.data_ptr() + offset * isz, lda,
+                dB.data_ptr() + offset * isz, ldb, beta, dC.data_ptr() + offset * isz, ldc)
+    got = host(dC)
+    ex, ab = oracle.gemm_exact(int(ta), int(tb), m, n, k, alpha, A[offset:], lda, B[offset:], ldb, beta, C0[offset:], ldc)
+    tol = gemm_tolerance(dtype, k, ab, ex)
+    err = np.abs(view(got[offset:], m, n, ldc).astype(np.float64) - ex)
+    assert np.all(err <= tol), f"max err {err.max():.3e} vs tol {tol.flat[err.argmax()]:.3e} kernel={handle.last_kernel()}"
+    # everything outside the m x n window (ld padding, leading offset) is untouched
+    mask = np.ones(got.shape, bool)
+    vm = view(mask[offset:], m, n, ldc)
+    vm[:] = False
+    assert np.array_equal(got[mask].view(np.uint8), C0[mask].view(np.uint8)), "wrote outside C's m x n window"
+    return err.max()
+
+
+OPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+@pytest.mark.parametrize("ta,tb", OPS)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_dgemm_reference_test_shapes(oracle, handle, ta, tb, variant):
+    handle.set_option("dgemm.variant", variant)
+    try:
+        # executor_test.cpp:15-17, planning_test.cpp:89-91/:121-123/:151-153, matrixop_test.cpp:34-36
+        for (m, n, k) in [(70, 45, 62), (23, 16, 35), (423, 125, 318), (69, 123, 42), (26, 27, 34)]:
+            _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.0, 0.0, 100 + m)
+            _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, -0.75, 0.5, 200 + m, lda_pad=3, ldb_pad=1, ldc_pad=2)
+    finally:
+        handle.set_option("dgemm.variant", 0)
+
+
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb):
+    for (m, n, k) in [(128, 128, 16), (129, 127, 17), (255, 257, 33), (1, 1, 1), (1, 300, 5), (300, 1, 7), (64, 64, 1),
+                      (130, 66, 129), (256, 384, 512)]:
+        _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.0, 0.0, 300 + m + n)
+    # odd leading dimensions (config 3 style) and a base pointer that is only 8 B aligned
+    _gemm_case(oracle, handle, np.float64, ta, tb, 257, 131, 65, 1.0, 0.0, 41, lda_pad=1, ldb_pad=1, ldc_pad=1)
+    _gemm_case(oracle, handle, np.float64, ta, tb, 200, 136, 72, 2.0, -1.0, 43, offset=1)
+    handle.set_option("dgemm.force_unaligned", 1)
+    try:
+        _gemm_case(oracle, handle, np.float64, ta, tb, 256, 128, 64, 1.0, 0.0, 47)
+    finally:
+        handle.set_option("dgemm.force_unaligned", 0)
+
+
+def test_dgemm_beta_zero_never_reads_c(oracle, handle):
+    # the reference hands uninitialised scratch as C with beta = 0 (matrixop.h:433-436)
+    for ta, tb in OPS:
+        _gemm_case(oracle, handle, np.float64, ta, tb, 150, 90, 40, 1.0, 0.0, 51, nan_c=True)
+
+
+def test_gemm_degenerate_cases(oracle, handle):
+    for dtype in (np.float64, np.float32):
+        # k == 0 and alpha == 0: C = beta*C without touching A/B
+        _gemm_case(oracle, handle, dtype, 0, 0, 37, 19, 0, 1.0, 0.5, 61)
+        _gemm_case(oracle, handle, dtype, 0, 0, 37, 19, 0, 1.0, 0.0, 62, nan_c=True)
+        _gemm_case(oracle, handle, dtype, 1, 0, 37, 19, 11, 0.0, -2.0, 63)
+        _gemm_case(oracle, handle, dtype, 0, 1, 37, 19, 11, 0.0, 1.0, 64)
+    one = 1.0
+    # m == 0 / n == 0 are no-ops; bad arguments give INVALID_VALUE (7), not a crash
+    assert handle.gemm(True, 0, 0, 0, 5, 5, one, None, 1, None, 5, one, None, 1, check=False) == 0
+    assert handle.gemm(True, 0, 0, 5, 0, 5, one, None, 5, None, 5, one, None, 5, check=False) == 0
+    x = torch.zeros(64, dtype=torch.float64, device="cuda")
+    assert handle.gemm(True, 0, 0, 8, 8, 8, one, x, 4, x, 8, one, x, 8, check=False) == 7   # lda < m
+    assert handle.gemm(True, 2, 0, 8, 8, 8, one, x, 8, x, 8, one, x, 8, check=False) == 7   # bad op
+    assert handle.gemm(True, 0, 0, -1, 8, 8, one, x, 8, x, 8, one, x, 8, check=False) == 7
+    assert handle.gemm(True, 0, 0, 8, 8, 8, one, None, 8, x, 8, one, x, 8, check=False) == 7  # null A
+
+
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_sgemm_reference_test_shapes(oracle, handle, ta, tb):
+    # executor_test.cpp:90-130 (the reference demands 1e-4 absolute at k = 62)
+    for (m, n, k) in [(70, 45, 62), (23, 16, 35), (129, 127, 65), (1, 1, 1), (260, 130, 40)]:
+        err = _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.0, 0.0, 400 + m)
+        if k <= 62:
+            assert err <= 1e-4
+        _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.5, -0.5, 500 + m, lda_pad=1, ldb_pad=2, ldc_pad=3)
+
+
+def test_dgemm_mid_size_against_oracle(oracle, handle):
+    # large enough for many CTAs and k-tiles, small enough for the long-double oracle (~1 s)
+    _gemm_case(oracle, handle, np.float64, 1, 0, 512, 384, 640, 1.0, 0.0, 71)
+    _gemm_case(oracle, handle, np.float64, 0, 1, 513, 383, 641, 1.0, 1.0, 73, lda_pad=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# geam: bit-exact against the oracle (which is pinned on cuBLAS geam outputs, tests/golden)
+# ---------------------------------------------------------------------------------------------
+def _geam_case(oracle, handle, dtype, ta, tb, m, n, alpha, beta, seed, lda_pad=0, ldb_pad=0, ldc_pad=0, inplace=False,
+               offset=0, nan_b=False):
+    ar, ac = (n, m) if ta else (m, n)
+    br, bc = (n, m) if tb else (m, n)
+    lda, ldb, ldc = ar + lda_pad, br + ldb_pad, m + ldc_pad
+    A = oracle.fill(lda * ac + offset, seed, dtype)
+    A[offset] = -0.0
+    B = oracle.fill(ldb * bc + offset, seed + 1, dtype)
+    if nan_b:
+        B[:] = np.nan
+    isz = A.itemsize
+    dA = dev(A)
+    if inplace:
+        assert not tb and ldb == ldc
+        C0 = B
+        dC = dev(C0)
+        dB = dC
+    else:
+        C0 = oracle.fill(ldc * n + offset, seed + 2, dtype)
+        dB, dC = dev(B), dev(C0)
+    handle.geam(dtype == np.float64, int(ta), int(tb), m, n, alpha, dA.data_ptr() + offset * isz, lda, beta,
+                dB.data_ptr() + offset * isz, ldb, dC.data_ptr() + offset * isz, ldc)
+    got = host(dC)
+    exp = C0.copy()
+    Bh = exp if inplace else B
+    oracle.geam(int(ta), int(tb), m, n, dtype(alpha), A[offset:], lda, dtype(beta), Bh[offset:], ldb, exp[offset:], ldc)
+    assert np.array_equal(got.view(np.uint8), exp.view(np.uint8)), f"geam mismatch kernel={handle.last_kernel()}"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_geam_move_shapes(oracle, handle, dtype):
+    # MatrixMove = geam(alpha, op(A), beta = 0, C aliases B) (matrixop.h:329-343); MoveTest 10x12 pad 32
+    _geam_case(oracle, handle, dtype, 0, 0, 10, 12, 1.0, 0.0, 1, ldb_pad=22, ldc_pad=22, inplace=True, nan_b=True)
+    _geam_case(oracle, handle, dtype, 1, 0, 25, 14, -2.0, 0.0, 2, ldb_pad=7, ldc_pad=7, inplace=True, nan_b=True)
+    _geam_case(oracle, handle, dtype, 1, 0, 23, 42, 0.5, 0.0, 3, ldb_pad=9, ldc_pad=9, inplace=True, nan_b=True)
+    for (m, n) in [(1, 1), (64, 64), (65, 63), (1, 777), (777, 1), (300, 517), (1024, 96), (130, 2050)]:
+        for ta in (0, 1):
+            _geam_case(oracle, handle, dtype, ta, 0, m, n, 1.0, 0.0, 10 + m, inplace=True, nan_b=True)
+            _geam_case(oracle, handle, dtype, ta, 0, m, n, 1.0, 0.0, 11 + m, lda_pad=1, ldb_pad=3, ldc_pad=3, inplace=True, nan_b=True)
+            _geam_case(oracle, handle, dtype, ta, 0, m, n, 1.0, 0.0, 12 + m, offset=1, inplace=True, nan_b=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_geam_accumulate_and_general(oracle, handle, dtype):
+    # MatrixAccumulate = in-place geam(1, op(S), beta, C) (matrixop.h:291-304)
+    for beta in (0.0, 1.0, 0.5, -1.25):
+        for ta in (0, 1):
+            _geam_case(oracle, handle, dtype, ta, 0, 29, 18, 1.0, beta, 20, lda_pad=2, ldb_pad=1, ldc_pad=1, inplace=True)
+            _geam_case(oracle, handle, dtype, ta, 0, 333, 129, 1.0, beta, 21, inplace=True)
+    # all four op pairs out of place, general alpha/beta, alpha == 0
+    for ta, tb in OPS:
+        for alpha, beta in [(0.3, -1.7), (-2.0, 1.0), (0.0, 0.6), (1.0, 0.0)]:
+            _geam_case(oracle, handle, dtype, ta, tb, 13, 7, alpha, beta, 30, lda_pad=1, ldb_pad=2, ldc_pad=3)
+            _geam_case(oracle, handle, dtype, ta, tb, 150, 210, alpha, beta, 31)
+
+
+def test_geam_argument_checks(handle):
+    x = torch.zeros(64, dtype=torch.float64, device="cuda")
+    y = torch.zeros(64, dtype=torch.float64, device="cuda")
+    assert handle.geam(True, 0, 0, 8, 8, 1.0, x, 4, 0.0, y, 8, y, 8, check=False) == 7       # lda < m
+    assert handle.geam(True, 1, 0, 8, 4, 1.0, x, 2, 0.0, y, 8, y, 8, check=False) == 7       # lda < n for op T
+    assert handle.geam(True, 1, 0, 8, 8, 1.0, x, 8, 0.0, y, 8, x, 8, check=False) == 7       # in-place transpose
+    assert handle.geam(True, 0, 0, 0, 8, 1.0, None, 1, 0.0, None, 1, None, 1, check=False) == 0
+
+
+def test_stream_binding_and_introspection(handle):
+    s = torch.cuda.Stream()
+    h2 = rt.Handle(stream=s)
+    assert h2.get_stream() == s.cuda_stream
+    n0 = h2.launch_count()
+    x = torch.ones(32 * 32, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    torch.cuda.synchronize()
+    h2.geam(True, 1, 0, 32, 32, 1.0, x, 32, 0.0, y, 32, y, 32)
+    s.synchronize()
+    assert h2.launch_count() == n0 + 1 and h2.last_kernel().startswith("geam_tile")
+    assert torch.equal(x, y)
+    h2.close()
+
+
+def test_fill_uniform_matches_oracle_generator(oracle, handle):
+    for dtype, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        x = torch.empty(100003, dtype=tdt, device="cuda")
+        handle.fill_uniform(x, 1234, -1.0, 1.0)
+        assert np.array_equal(host(x), oracle.fill(100003, 1234, dtype))

@@ -81,8 +81,8 @@ int rtat_b200_sgemm(rtat_b200_handle_t handle, int transa, int transb, int m, in
  * C is m x n.  The reference always calls this with transb == N and C aliasing B (in place,
  * ldb == ldc; matrixop.h:302,340-341); that aliasing is supported.  C aliasing A is supported only
  * for transa == N with lda == ldc.  beta == 0 means B is never read; alpha == 0 means A is never
- * read.  Results are bit-identical to cuBLAS geam: one rounding of alpha*a, one of beta*b, one of
- * the sum (no FMA contraction) — verified against the reference executor, see tests/golden. */
+ * read.  Results are bit-identical to cuBLAS 12.9 geam: c = fma(beta, b, RN(alpha*a)) in the
+ * general case — pinned against the reference executor's outputs, see tests/golden. */
 int rtat_b200_dgeam(rtat_b200_handle_t handle, int transa, int transb, int m, int n,
                     const double *alpha, const double *A, int lda, const double *beta,
                     const double *B, int ldb, double *C, int ldc);

@@ -1,6 +1,7 @@
 /* oracle.c — see oracle.h.  TEST INFRASTRUCTURE ONLY: CPU restatement of the reference algorithm. */
 #include "oracle.h"
 #include <string.h>
+#include <math.h>
 
 static int roundup(int x, int pad) { return ((x + pad - 1) / pad) * pad; }
 
@@ -46,18 +47,22 @@ size_t oracle_gemm_plan_workspace(const char *plan, int transa, int transb, int 
 #define T double
 #define SUF d
 #define WIDE long double
+#define FMA fma
 #include "oracle_impl.inc"
 #undef T
 #undef SUF
 #undef WIDE
+#undef FMA
 
 #define T float
 #define SUF s
 #define WIDE double
+#define FMA fmaf
 #include "oracle_impl.inc"
 #undef T
 #undef SUF
 #undef WIDE
+#undef FMA
 
 static uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

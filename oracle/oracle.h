@@ -40,7 +40,8 @@ void oracle_sgemm_exact(int transa, int transb, int m, int n, int k, float alpha
 
 /* cuBLAS geam as the reference calls it (src/matrix_ops/matrixop.h:111-140, :291-304, :329-343):
  * C = alpha*op(A) + beta*op(B), m x n.  beta == 0: B not read, c = alpha*a;  alpha == 0: A not
- * read, c = beta*b;  otherwise c = RN(RN(alpha*a) + RN(beta*b)) (rounding pinned by tests/golden). */
+ * read, c = beta*b;  otherwise c = fma(beta, b, RN(alpha*a)) — the rounding cuBLAS 12.9 geam shows on
+ * a B200, pinned bit-for-bit by tests/golden (mul+mul+add and fma(alpha,a,RN(beta*b)) both mismatch). */
 void oracle_dgeam(int transa, int transb, int m, int n, double alpha, const double *A, int lda,
                   double beta, const double *B, int ldb, double *C, int ldc);
 void oracle_sgeam(int transa, int transb, int m, int n, float alpha, const float *A, int lda,

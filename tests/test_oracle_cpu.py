@@ -4,6 +4,7 @@ arithmetic, plan algebra (reference src/methods/gemm.cpp:82-134,182-221), worksp
 executor itself (tests/golden/reference_b200.*)."""
 import json
 import os
+from fractions import Fraction
 
 import numpy as np
 import pytest
@@ -76,8 +77,13 @@ def test_geam_definition_and_aliasing(oracle, dtype):
             oracle.geam(ta, tb, m, n, al, A, ar + 1, be, B, br + 2, Cm, m + 3)
             Av, Bv = view(A, ar, ac, ar + 1), view(B, br, bc, br + 2)
             opA, opB = (Av.T if ta else Av), (Bv.T if tb else Bv)
-            exp = (al * opA).astype(dtype) + (be * opB).astype(dtype)
-            assert np.array_equal(view(Cm, m, n, m + 3), exp.astype(dtype))
+            pa = (al * opA).astype(dtype)
+            if dtype == np.float32:  # float64 holds the product exactly => one rounding, i.e. an fma
+                exp = (np.float64(be) * opB.astype(np.float64) + pa.astype(np.float64)).astype(dtype)
+            else:  # exact rational arithmetic, correctly rounded once
+                exp = np.array([[float(Fraction(float(be)) * Fraction(float(opB[i, j])) + Fraction(float(pa[i, j])))
+                                 for j in range(n)] for i in range(m)])
+            assert np.array_equal(view(Cm, m, n, m + 3), exp)
             assert np.all(view(Cm, m + 3, n, m + 3)[m:] == 7.0)
     # beta == 0: B is never read (may be NaN), alpha == 1 is a bit-exact copy incl. -0.0
     A = oracle.fill(m * n, 8, dtype)
@@ -88,7 +94,7 @@ def test_geam_definition_and_aliasing(oracle, dtype):
     # in place accumulate (reference matrixop.h:302): B = A^T + beta*B
     S = oracle.fill(n * m, 9, dtype)
     Bc = oracle.fill(m * n, 10, dtype)
-    exp = view(S, n, m, n).T + (dtype(0.5) * view(Bc, m, n, m)).astype(dtype)
+    exp = view(S, n, m, n).T + (dtype(0.5) * view(Bc, m, n, m)).astype(dtype)  # 0.5*b is exact
     oracle.geam(1, 0, m, n, dtype(1), S, n, dtype(0.5), Bc, m, Bc, m)
     assert np.array_equal(view(Bc, m, n, m), exp.astype(dtype))
 

@@ -78,6 +78,7 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   cudaStreamSynchronize(h->stream);
   if (h->arena) cudaFree(h->arena);
   if (h->staging) cudaFree(h->staging);
+  if (h->sk_flags) cudaFree(h->sk_flags);
   if (h->staging_done) cudaEventDestroy(h->staging_done);
   delete h;
   return RTAT_B200_STATUS_SUCCESS;
@@ -229,6 +230,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   if (need > h->staging_bytes) {
     cudaStreamSynchronize(h->stream);
     if (h->staging) cudaFree(h->staging);
+  if (h->sk_flags) cudaFree(h->sk_flags);
     h->staging = nullptr;
     h->staging_bytes = 0;
     if (cudaMalloc(&h->staging, need) != cudaSuccess) {

@@ -20,6 +20,9 @@ struct rtat_b200_context {
   // introspection
   const char *last_kernel = "none";
   uint64_t launches = 0;
+  // stream-K fix-up flags (1024 x u32) and the generation they are compared against
+  void *sk_flags = nullptr;
+  unsigned sk_generation = 0;
   // host-entry staging
   void *staging = nullptr;
   size_t staging_bytes = 0;

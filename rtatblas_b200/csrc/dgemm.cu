@@ -218,6 +218,9 @@ static int launch_ops(rtat_b200_context *h, DgemmParams &p, int variant) {
   return launch_cfg<128, 128, 16, 64, 32, 4, TA, TB, ALIGNED>(h, p, ALIGNED ? "dgemm_dmma_128x128x16_cpasync16" : "dgemm_dmma_128x128x16_cpasync8");
 }
 
+int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma);
+
 int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, double alpha,
           const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc) {
   if (k == 0 || alpha == 0.0) {
@@ -237,11 +240,17 @@ int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, dou
   bool aligned = al16(A, lda) && al16(B, ldb);
   int variant = opt(h, "dgemm.variant");
   if (opt(h, "dgemm.force_unaligned")) aligned = false;
+  // variants: 1/2 = cp.async multistage kernels (128x128 / 64x64 tiles, this file);
+  //           3 = persistent warp-specialised kernel, TMA producers when the operands allow it;
+  //           4 = same with the cp.async producers forced (dgemm_ws.cu)
   if (variant == 0) {
-    // heuristic: 128x128 tiles need >= ~1 wave of CTAs to beat 64x64
-    long long big_tiles = (long long)((m + 127) / 128) * ((n + 127) / 128);
-    variant = big_tiles >= h->sm_count ? 1 : 2;
+    // the persistent stream-K kernel fills the machine from ~1 tile x 32 k-tiles upward; below that
+    // (a handful of k-tiles in total) the small-tile multistage kernel has less fixed cost
+    long long units = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16);
+    variant = units >= 64 ? 3 : 2;
   }
+  if (variant == 3 || variant == 4)
+    return dgemm_ws(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, variant == 3 && !opt(h, "dgemm.force_unaligned"));
 #define RTAT_DISPATCH(TA_, TB_)                                                            \
   (aligned ? launch_ops<TA_, TB_, true>(h, p, variant) : launch_ops<TA_, TB_, false>(h, p, variant))
   if (!ta && !tb) return RTAT_DISPATCH(false, false);

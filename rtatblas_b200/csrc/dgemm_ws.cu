@@ -1,0 +1,524 @@
+// Persistent, warp-specialised DGEMM for sm_100a:  C = alpha * op(A) * op(B) + beta * C
+//
+// Replaces cublasDgemm behind MatrixMult / MatrixMultAlloc (reference src/matrix_ops/matrixop.h:15-46,
+// :347-440).  FP64 has no tcgen05 kind, so the math is DMMA.8x8x4 issued by eight consumer warps; what
+// is Blackwell/Hopper-style here is the data path:
+//
+//   producer   TMA (cp.async.bulk.tensor, 128 B swizzle) issued by ONE elected thread into a
+//              6-stage shared-memory ring guarded by full/empty mbarriers.  The operand's stored
+//              orientation is consumed in place: a K-contiguous operand (op T for A, op N for B) is
+//              one [16 k] x [128 rows] box per stage, an M/N-contiguous operand eight [16 mn] x [16 k]
+//              boxes.  This is the "transpose folded into the TMA descriptor" plan variant.
+//              Operands TMA cannot address (base not 16 B aligned or odd ld, e.g. 4097/3001 in
+//              config 3) are fed by four producer warps with 8-byte cp.async that complete on the same
+//              mbarriers and write the same swizzled layout ("pad folded into the load").
+//   consumers  8 warps, 64x32 accumulator tile each (64 FP64 registers), fragments read with
+//              conflict-free LDS.64: rows/columns of each 8x8 DMMA block are assigned to lanes
+//              through a permutation chosen so that the 16 lanes of a half-warp hit 16 different
+//              8-byte bank pairs under the 128 B swizzle (see frag_*).  No __syncthreads in the main
+//              loop; the only per-k-tile synchronisation is one mbarrier wait and one arrive per warp.
+//   schedule   persistent, hybrid stream-K: the last (#tiles mod #CTAs) + #CTAs tiles are cut into equal
+//              runs of k-tiles, one run per CTA, so every SM finishes at the same time instead of
+//              idling through a ragged last wave (and a 1024^3 problem, 64 tiles, still occupies all
+//              148 SMs).  A CTA whose run starts inside a tile stores its accumulators, fragment-major,
+//              to a per-CTA slot in the handle's arena and raises a flag; the CTA that owns the tile's
+//              first k-tile finishes last, adds the slots in CTA order (deterministic) and runs the
+//              epilogue.  The remaining tiles are data-parallel: CTA c walks tiles c, c+grid, ... in a
+//              grouped raster so resident CTAs share operand strips in L2.  The producer runs ahead
+//              across segment boundaries, so the ring is full when the consumers leave an epilogue.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace rtat_b200 {
+
+namespace ws {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 6;
+constexpr int WM = 64, WN = 32;                 // consumer warp tile
+constexpr int CONSUMER_WARPS = (BM / WM) * (BN / WN);  // 8
+constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CPASYNC_PRODUCER_WARPS = 4;
+constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  int m, n, k;
+  const double *A;
+  int lda;
+  const double *B;
+  int ldb;
+  double *C;
+  int ldc;
+  double alpha, beta;
+  int tiles_m, tiles_n, num_tiles, kt;
+  // hybrid stream-K schedule (host-computed): tiles [0, dp_tiles) are data-parallel, tiles
+  // [dp_tiles, num_tiles) are covered by sk_units = sk_tiles * kt k-tile units split evenly
+  int dp_tiles;
+  long long sk_units;
+  double *sk_slots;        // gridDim.x slots of CONSUMER_WARPS*32*64 doubles
+  unsigned *sk_flags;      // gridDim.x flags, compared against sk_generation
+  unsigned sk_generation;
+};
+
+// One contiguous piece of work: k-tiles [kb, ke) of `tile`.
+struct Segment {
+  int tile, kb, ke;
+};
+
+// Walks the segments of CTA `cta`: first its stream-K run (cut at tile boundaries), then its
+// data-parallel tiles.  Producer and consumers iterate with identical state.
+struct SegmentIter {
+  long long u, u1;
+  int next_dp, P, dp_tiles, kt;
+  __device__ SegmentIter(const Params &p, int cta, int nctas)
+      : u(p.sk_units * cta / nctas), u1(p.sk_units * (cta + 1) / nctas), next_dp(cta), P(nctas), dp_tiles(p.dp_tiles), kt(p.kt) {}
+  __device__ bool next(Segment &s) {
+    if (u < u1) {
+      int t = int(u / kt);
+      s.kb = int(u - (long long)t * kt);
+      long long rem = u1 - u;
+      s.ke = (rem < kt - s.kb) ? s.kb + int(rem) : kt;
+      s.tile = dp_tiles + t;
+      u += s.ke - s.kb;
+      return true;
+    }
+    if (next_dp < dp_tiles) {
+      s.tile = next_dp;
+      s.kb = 0;
+      s.ke = kt;
+      next_dp += P;
+      return true;
+    }
+    return false;
+  }
+};
+
+// ---- mbarrier / TMA primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// ---- lane <-> element permutations ----------------------------------------------------------------
+// K-contiguous operand: rows (m or n) are 128 B smem rows swizzled by (row & 7).  Lane index x (0..7)
+// of a DMMA block owns physical row rho(x) of the block.
+__host__ __device__ constexpr int rho(int x) { return 2 * (x & 3) + (x >> 2); }
+// M/N-contiguous operand: 16 consecutive m (or n) form one 128 B smem row per k, swizzled by (k & 7);
+// a pair of DMMA blocks (b = 0,1) shares one 16-wide atom.  Lane index x of block b owns element
+// rho2(b, x) of the atom.
+__host__ __device__ constexpr int rho2(int b, int x) { return 4 * b + (x & 1) + 8 * ((x >> 1) & 1) + 2 * (x >> 2); }
+
+// physical index (within the warp tile) of DMMA block `blk`, lane index x
+template <bool KC>
+__host__ __device__ constexpr int phys_index(int blk, int x) {
+  return KC ? 8 * blk + rho(x) : 16 * (blk / 2) + rho2(blk & 1, x);
+}
+
+// swizzled byte offset of element (mn, k) of an operand tile (what TMA produces; the cp.async
+// producers write the same layout)
+template <bool KC>
+__device__ __forceinline__ uint32_t tile_offset(int mn, int k) {
+  if (KC) return mn * 128 + ((((k >> 1) ^ (mn & 7)) & 7) << 4) + ((k & 1) << 3);
+  return (mn >> 4) * (BK * 128) + k * 128 + (((((mn & 15) >> 1) ^ (k & 7)) & 7) << 4) + ((mn & 1) << 3);
+}
+
+// Per-thread fragment addressing for one operand: addr(blk, ks) = base + imm(blk, ks) + off[sel(blk, ks)]
+template <bool KC>
+struct FragAddr {
+  uint32_t base;
+  uint32_t off[4];
+  __device__ __forceinline__ void init(uint32_t tile_base_warp /* byte offset of the warp's first row */, int q, int x) {
+    if (KC) {
+      int r = rho(x);
+      int t = (q >> 1) ^ r;
+      base = tile_base_warp + r * 128 + ((q & 1) << 3);
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) off[ks] = uint32_t(((2 * ks) ^ t) & 7) << 4;
+    } else {
+      int t = ((((x >> 1) & 1) << 2) + (x >> 2)) ^ q;
+      base = tile_base_warp + q * 128 + ((x & 1) << 3);
+#pragma unroll
+      for (int u = 0; u < 4; u++) off[u] = uint32_t(((2 * u) ^ t) & 7) << 4;
+    }
+  }
+  __device__ __forceinline__ uint32_t addr(int blk, int ks) const {
+    if (KC) return base + blk * 1024 + off[ks];
+    return base + (blk >> 1) * (BK * 128) + ks * 512 + off[(blk & 1) | ((ks & 1) << 1)];
+  }
+};
+
+// cp.async producer: one 128 x BK operand tile per call, 128 threads, 16 elements each.  Element
+// ownership is chosen so that everything but one add (and one xor for M/N-contiguous operands) per
+// element is loop-invariant: K-contiguous -> thread owns column kk = pt % 16 of rows pt/16 + 8i
+// (row & 7 is constant, so the swizzle term is too); M/N-contiguous -> thread owns element pt of k-row i.
+template <bool KC>
+__device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *__restrict__ X, int ld, int mn0, int k0,
+                                                      int MN, int K, int pt) {
+  constexpr int PT = CPASYNC_PRODUCER_WARPS * 32;
+  constexpr int PER = 128 * BK / PT;
+  static_assert(PT == 128, "ownership pattern below assumes 128 producer threads");
+  if (KC) {
+    const int kk = pt % BK, r0 = pt / BK;
+    const bool kok = (k0 + kk) < K;
+    const double *src0 = X + (size_t)(mn0 + r0) * ld + (k0 + kk);
+    const size_t step = (size_t)(PT / BK) * ld;
+    const uint32_t dst0 = s + tile_offset<true>(r0, kk);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      bool ok = kok && (mn0 + r0 + (PT / BK) * i) < MN;
+      cp_async8_zfill(dst0 + i * (PT / BK) * 128, ok ? src0 + i * step : X, ok ? 8 : 0);
+    }
+  } else {
+    const bool mok = (mn0 + pt) < MN;
+    const double *src0 = X + (size_t)k0 * ld + (mn0 + pt);
+    const uint32_t dst0 = s + (pt >> 4) * (BK * 128) + ((pt & 1) << 3);
+    const uint32_t c = (pt & 15) >> 1;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      bool ok = mok && (k0 + i) < K;
+      cp_async8_zfill(dst0 + i * 128 + ((c ^ (i & 7)) << 4), ok ? src0 + (size_t)i * ld : X, ok ? 8 : 0);
+    }
+  }
+}
+
+template <bool TA, bool TB, bool USE_TMA>
+__global__ void __launch_bounds__((CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, 1)
+dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+  constexpr bool KCA = TA;    // op(A)(m,k): stored k x m when transposed => k contiguous
+  constexpr bool KCB = !TB;   // op(B)(k,n): stored k x n when not transposed => k contiguous
+  constexpr int PRODUCER_THREADS = USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS * 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_base + 8 * s, PRODUCER_THREADS);
+      mbar_init(bar_base + 8 * (STAGES + s), CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_coords = [&](int tile, int &m0, int &n0) {
+    constexpr int GROUP = 8;
+    int group_size = GROUP * p.tiles_n;
+    int first_m = (tile / group_size) * GROUP;
+    int gm = min(p.tiles_m - first_m, GROUP);
+    m0 = (first_m + (tile % group_size) % gm) * BM;
+    n0 = ((tile % group_size) / gm) * BN;
+  };
+
+  if (warp >= CONSUMER_WARPS) {
+    // ======================= producer =======================
+    int stage = 0;
+    uint32_t phase = 0;
+    if (USE_TMA) {
+      if (warp == CONSUMER_WARPS && lane == 0) {
+        SegmentIter it(p, blockIdx.x, gridDim.x);
+        Segment seg;
+        while (it.next(seg)) {
+          int m0, n0;
+          tile_coords(seg.tile, m0, n0);
+          for (int kt = seg.kb; kt < seg.ke; kt++) {
+            mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
+            uint32_t full = bar_base + 8 * stage;
+            uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
+            mbar_arrive_expect_tx(full, STAGE_BYTES);
+            int k0 = kt * BK;
+            if (KCA) {
+              tma_load_2d(sA, &mapA, k0, m0, full);
+            } else {
+#pragma unroll
+              for (int b = 0; b < BM / 16; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 16 * b, k0, full);
+            }
+            if (KCB) {
+              tma_load_2d(sB, &mapB, k0, n0, full);
+            } else {
+#pragma unroll
+              for (int b = 0; b < BN / 16; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 16 * b, k0, full);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else {
+      const int pt = threadIdx.x - CONSUMER_WARPS * 32;  // 0..127
+      SegmentIter it(p, blockIdx.x, gridDim.x);
+      Segment seg;
+      while (it.next(seg)) {
+        int m0, n0;
+        tile_coords(seg.tile, m0, n0);
+        for (int kt = seg.kb; kt < seg.ke; kt++) {
+          mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
+          uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
+          issue_operand_cpasync<KCA>(sA, p.A, p.lda, m0, kt * BK, p.m, p.k, pt);
+          issue_operand_cpasync<KCB>(sB, p.B, p.ldb, n0, kt * BK, p.n, p.k, pt);
+          cp_async_mbar_arrive_noinc(bar_base + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
+    }
+    return;
+  }
+
+  // ======================= consumers =======================
+  constexpr int MI = WM / 8, NI = WN / 8, KS = BK / 4;
+  const int q = lane % 4, g = lane / 4;
+  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+  FragAddr<KCA> fa_addr;
+  FragAddr<KCB> fb_addr;
+  fa_addr.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
+  fb_addr.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
+
+  int stage = 0;
+  uint32_t phase = 0;
+  const double alpha = p.alpha, beta = p.beta;
+
+  SegmentIter it(p, blockIdx.x, gridDim.x);
+  Segment seg;
+  const int ctid = threadIdx.x;  // 0..255 (consumer threads come first)
+  constexpr int SLOT_DOUBLES = CONSUMER_WARPS * 32 * MI * NI * 2;
+  while (it.next(seg)) {
+    int m0, n0;
+    tile_coords(seg.tile, m0, n0);
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = seg.kb; kt < seg.ke; kt++) {
+      mbar_wait(bar_base + 8 * stage, phase);
+      const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+      double fa[2][MI], fb[2][NI];
+#pragma unroll
+      for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa_addr.addr(i, 0));
+#pragma unroll
+      for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb_addr.addr(j, 0));
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (ks + 1 < KS) {
+#pragma unroll
+          for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa_addr.addr(i, ks + 1));
+#pragma unroll
+          for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb_addr.addr(j, ks + 1));
+        }
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+          for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[cur][i], fb[cur][j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    if (seg.kb > 0) {
+      // stream-K contributor: this run started inside the tile.  Park the accumulators
+      // (fragment-major, coalesced) in this CTA's slot and publish them.
+      double *slot = p.sk_slots + (size_t)blockIdx.x * SLOT_DOUBLES + ctid;
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+          __stcg(slot + ((i * NI + j) * 2 + 0) * (CONSUMER_WARPS * 32), acc[i][j][0]);
+          __stcg(slot + ((i * NI + j) * 2 + 1) * (CONSUMER_WARPS * 32), acc[i][j][1]);
+        }
+      __threadfence();
+      asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_WARPS * 32) : "memory");
+      if (ctid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p.sk_flags + blockIdx.x), "r"(p.sk_generation) : "memory");
+      continue;
+    }
+    if (seg.ke < p.kt) {
+      // stream-K finisher: owns the tile's first k-tile; the CTAs after this one cover the rest of
+      // the tile and parked their parts early in their runs.  Add them in CTA order.
+      const long long tile_end = (long long)(seg.tile - p.dp_tiles + 1) * p.kt;
+      for (int c = blockIdx.x + 1; c < (int)gridDim.x && p.sk_units * c / (long long)gridDim.x < tile_end; c++) {
+        if (ctid == 0) {
+          unsigned v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.sk_flags + c) : "memory");
+          } while (v != p.sk_generation);
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_WARPS * 32) : "memory");
+        const double *slot = p.sk_slots + (size_t)c * SLOT_DOUBLES + ctid;
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+          for (int j = 0; j < NI; j++) {
+            acc[i][j][0] += __ldcg(slot + ((i * NI + j) * 2 + 0) * (CONSUMER_WARPS * 32));
+            acc[i][j][1] += __ldcg(slot + ((i * NI + j) * 2 + 1) * (CONSUMER_WARPS * 32));
+          }
+      }
+    }
+
+    // epilogue: lane (q,g) of block (i,j) holds C[row(i,g)][col(j,2q+e)]
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int col = n0 + wn0 + phys_index<KCB>(j, 2 * q + e);
+        if (col >= p.n) continue;
+        double *ccol = p.C + (size_t)col * p.ldc;
+#pragma unroll
+        for (int i = 0; i < MI; i++) {
+          int row = m0 + wm0 + phys_index<KCA>(i, g);
+          if (row < p.m) {
+            double v = alpha * acc[i][j][e];
+            if (beta != 0.0) v += beta * ccol[row];
+            ccol[row] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+static bool make_map(CUtensorMap *map, const double *base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
+                     uint32_t box0, uint32_t box1) {
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld_elems * sizeof(double)};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <bool TA, bool TB, bool USE_TMA>
+static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap &ma, const CUtensorMap &mb, const char *name) {
+  auto kern = dgemm_ws_kernel<TA, TB, USE_TMA>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_INTERNAL_ERROR;
+    }
+    configured = true;
+  }
+  int threads = (CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32;
+  kern<<<grid, threads, SMEM_BYTES, h->stream>>>(ma, mb, p);
+  return check_launch(h, name);
+}
+
+}  // namespace ws
+
+bool dgemm_ws_tma_ok(const double *A, int lda, const double *B, int ldb) {
+  auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 2 == 0; };
+  return ok(A, lda) && ok(B, ldb);
+}
+
+int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma) {
+  using namespace ws;
+  Params p{};
+  p.m = m; p.n = n; p.k = k;
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+  p.alpha = alpha; p.beta = beta;
+  p.tiles_m = (m + BM - 1) / BM;
+  p.tiles_n = (n + BN - 1) / BN;
+  long long tiles = (long long)p.tiles_m * p.tiles_n;
+  if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  p.num_tiles = (int)tiles;
+  p.kt = (k + BK - 1) / BK;
+  // ---- schedule: hybrid stream-K ---------------------------------------------------------------
+  // grid: one CTA per SM, fewer when there are not even MIN_UNITS k-tiles of work per CTA.
+  constexpr int MIN_UNITS = 4;
+  long long units = tiles * p.kt;
+  int grid = h->sm_count;
+  if (units < (long long)grid * MIN_UNITS) grid = (int)((units + MIN_UNITS - 1) / MIN_UNITS);
+  if (grid < 1) grid = 1;
+  int sk_mode = opt(h, "dgemm.streamk", 1);  // 0 = data-parallel only (for A/B measurements)
+  int rem = p.num_tiles % grid;
+  int sk_tiles = 0;
+  if (sk_mode && (rem != 0 || p.num_tiles < grid) && p.kt >= 8) {
+    // cover the ragged wave plus one full wave, so every CTA's run is 1-2 tiles long
+    sk_tiles = p.num_tiles <= grid ? p.num_tiles : rem + grid;
+    if (sk_tiles > p.num_tiles) sk_tiles = p.num_tiles;
+  }
+  if (!sk_tiles && p.num_tiles < grid) grid = p.num_tiles;
+  p.dp_tiles = p.num_tiles - sk_tiles;
+  p.sk_units = (long long)sk_tiles * p.kt;
+  if (sk_tiles) {
+    size_t slot_bytes = sizeof(double) * CONSUMER_WARPS * 32 * 64;
+    int st = ensure_arena(h, slot_bytes * grid);
+    if (st) return st;
+    if (!h->sk_flags) {
+      if (cudaMalloc(&h->sk_flags, 4096) != cudaSuccess || cudaMemsetAsync(h->sk_flags, 0, 4096, h->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return RTAT_B200_STATUS_ALLOC_FAILED;
+      }
+      h->sk_generation = 0;
+    }
+    p.sk_slots = static_cast<double *>(h->arena);
+    p.sk_flags = static_cast<unsigned *>(h->sk_flags);
+    p.sk_generation = ++h->sk_generation;
+  }
+  bool use_tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof ma);
+  memset(&mb, 0, sizeof mb);
+  if (use_tma) {
+    bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM) : make_map(&ma, A, m, k, lda, 16, BK);
+    ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN) : make_map(&mb, B, n, k, ldb, 16, BK));
+    if (!ok) use_tma = false;  // e.g. strides beyond the descriptor's range: take the cp.async producers
+  }
+#define RTAT_WS(TA_, TB_)                                                                                   \
+  (use_tma ? launch<TA_, TB_, true>(h, p, grid, ma, mb, sk_tiles ? "dgemm_ws_dmma_128x128x16_tma_streamk" : "dgemm_ws_dmma_128x128x16_tma") \
+           : launch<TA_, TB_, false>(h, p, grid, ma, mb, sk_tiles ? "dgemm_ws_dmma_128x128x16_cpasync8_streamk" : "dgemm_ws_dmma_128x128x16_cpasync8"))
+  if (!ta && !tb) return RTAT_WS(false, false);
+  if (ta && !tb) return RTAT_WS(true, false);
+  if (!ta && tb) return RTAT_WS(false, true);
+  return RTAT_WS(true, true);
+#undef RTAT_WS
+}
+
+}  // namespace rtat_b200

@@ -44,7 +44,7 @@ OPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
 
 
 @pytest.mark.parametrize("ta,tb", OPS)
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_dgemm_reference_test_shapes(oracle, handle, ta, tb, variant):
     handle.set_option("dgemm.variant", variant)
     try:
@@ -57,7 +57,16 @@ def test_dgemm_reference_test_shapes(oracle, handle, ta, tb, variant):
 
 
 @pytest.mark.parametrize("ta,tb", OPS)
-def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb):
+@pytest.mark.parametrize("variant", [0, 3])
+def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb, variant):
+    handle.set_option("dgemm.variant", variant)
+    try:
+        _dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb)
+    finally:
+        handle.set_option("dgemm.variant", 0)
+
+
+def _dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb):
     for (m, n, k) in [(128, 128, 16), (129, 127, 17), (255, 257, 33), (1, 1, 1), (1, 300, 5), (300, 1, 7), (64, 64, 1),
                       (130, 66, 129), (256, 384, 512)]:
         _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.0, 0.0, 300 + m + n)
@@ -105,10 +114,17 @@ def test_sgemm_reference_test_shapes(oracle, handle, ta, tb):
         _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.5, -0.5, 500 + m, lda_pad=1, ldb_pad=2, ldc_pad=3)
 
 
-def test_dgemm_mid_size_against_oracle(oracle, handle):
+@pytest.mark.parametrize("variant", [0, 3, 4])
+def test_dgemm_mid_size_against_oracle(oracle, handle, variant):
     # large enough for many CTAs and k-tiles, small enough for the long-double oracle (~1 s)
-    _gemm_case(oracle, handle, np.float64, 1, 0, 512, 384, 640, 1.0, 0.0, 71)
-    _gemm_case(oracle, handle, np.float64, 0, 1, 513, 383, 641, 1.0, 1.0, 73, lda_pad=1)
+    handle.set_option("dgemm.variant", variant)
+    try:
+        _gemm_case(oracle, handle, np.float64, 1, 0, 512, 384, 640, 1.0, 0.0, 71)
+        _gemm_case(oracle, handle, np.float64, 0, 1, 513, 383, 641, 1.0, 1.0, 73, lda_pad=1)
+        _gemm_case(oracle, handle, np.float64, 0, 0, 1100, 2300, 200, 1.0, 0.0, 75)   # > 148 tiles: persistent loop
+        _gemm_case(oracle, handle, np.float64, 1, 1, 2300, 1100, 200, -1.0, 0.5, 77, ldb_pad=2)
+    finally:
+        handle.set_option("dgemm.variant", 0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -199,3 +215,60 @@ def test_fill_uniform_matches_oracle_generator(oracle, handle):
         x = torch.empty(100003, dtype=tdt, device="cuda")
         handle.fill_uniform(x, 1234, -1.0, 1.0)
         assert np.array_equal(host(x), oracle.fill(100003, 1234, dtype))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full-size configs: the reference's arithmetic at these sizes is cuBLAS, which
+# torch.matmul reaches here (test-only use).  Both sides obey the stated bound against the exact
+# product, so they may differ from each other by at most twice the bound.
+# ---------------------------------------------------------------------------------------------
+def _full_size_vs_cublas(handle, dtype, ta, tb, m, n, k, seed, streamk=1):
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    A = torch.empty(ar * ac, dtype=tdt, device="cuda")
+    B = torch.empty(br * bc, dtype=tdt, device="cuda")
+    handle.fill_uniform(A, seed)
+    handle.fill_uniform(B, seed + 1)
+    Cm = torch.full((m * n,), float("nan"), dtype=tdt, device="cuda")
+    handle.set_option("dgemm.streamk", streamk)
+    try:
+        handle.gemm(dtype == np.float64, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+    finally:
+        handle.set_option("dgemm.streamk", 1)
+    # column-major (rows, cols, ld=rows) buffer == row-major (cols, rows) tensor
+    Am, Bm = A.view(ac, ar).t(), B.view(bc, br).t()
+    opA, opB = (Am.t() if ta else Am), (Bm.t() if tb else Bm)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = opA @ opB
+        bound = opA.abs() @ opB.abs()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    got = Cm.view(n, m).t()
+    eps = np.finfo(dtype).eps
+    c = 2 if dtype == np.float64 else 8
+    tol = 2 * c * k * eps * bound + eps * ref.abs()
+    err = (got - ref).abs()
+    assert bool(torch.all(err <= tol)), f"max err {err.max().item():.3e} kernel={handle.last_kernel()}"
+    return handle.last_kernel()
+
+
+def test_dgemm_config1_1024_cubed(handle):
+    assert "streamk" in _full_size_vs_cublas(handle, np.float64, 0, 0, 1024, 1024, 1024, 9001)
+    _full_size_vs_cublas(handle, np.float64, 0, 0, 1024, 1024, 1024, 9001, streamk=0)
+
+
+def test_dgemm_config3_unaligned(handle):
+    # m=4097 n=3001 k=2049 op NT: odd leading dimensions => cp.async producers, ragged tiles, stream-K
+    assert "cpasync8" in _full_size_vs_cublas(handle, np.float64, 0, 1, 4097, 3001, 2049, 9003)
+
+
+def test_dgemm_config2_8192_tn(handle):
+    assert "tma" in _full_size_vs_cublas(handle, np.float64, 1, 0, 8192, 8192, 8192, 9002)
+
+
+def test_dgemm_config5_column_block(handle):
+    # one GPU's share of config 5 at 8 GPUs, scaled to fit the test budget: m=k=8192, n=1024
+    _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)

@@ -20,7 +20,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/rtat_b200.h
 
 $(LIBDIR)/librtat_b200.so: $(KERNEL_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcuda -Xlinker -rpath,$(CUDA_HOME)/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -rpath,$(CUDA_HOME)/lib64
 
 host: $(LIBDIR)/librtat_b200.so
 	@if [ -f rtatblas_b200/host/Makefile ]; then $(MAKE) --no-print-directory -C rtatblas_b200/host; fi

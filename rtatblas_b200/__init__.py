@@ -17,3 +17,4 @@ from ._capi import (  # noqa: F401
     lib_path,
     exported_symbols,
 )
+from ._host import Planner, host_lib, host_lib_path  # noqa: F401

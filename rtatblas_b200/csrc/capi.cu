@@ -7,6 +7,19 @@
 using namespace rtat_b200;
 
 namespace rtat_b200 {
+void *tensor_map_encoder_raw() {
+  static void *fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+    }
+    return p;
+  }();
+  return fn;
+}
+
 int ensure_arena(rtat_b200_context *h, size_t bytes) {
   if (bytes <= h->arena_bytes) return RTAT_B200_STATUS_SUCCESS;
   if (h->arena) {
@@ -230,7 +243,6 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   if (need > h->staging_bytes) {
     cudaStreamSynchronize(h->stream);
     if (h->staging) cudaFree(h->staging);
-  if (h->sk_flags) cudaFree(h->sk_flags);
     h->staging = nullptr;
     h->staging_bytes = 0;
     if (cudaMalloc(&h->staging, need) != cudaSuccess) {
@@ -243,19 +255,23 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   T *dA = reinterpret_cast<T *>(base), *dB = reinterpret_cast<T *>(base + bytes_a),
     *dC = reinterpret_cast<T *>(base + bytes_a + bytes_b);
   cudaStream_t s = h->stream;
-  if (cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-      cudaMemcpyAsync(dB, B, sizeof(T) * ldb * cols_b, cudaMemcpyHostToDevice, s) != cudaSuccess)
+  auto cuda_ok = [](cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    fprintf(stderr, "rtat_b200 host entry: %s: %s\n", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return false;
+  };
+  if (!cuda_ok(cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, s), "H2D A") ||
+      !cuda_ok(cudaMemcpyAsync(dB, B, sizeof(T) * ldb * cols_b, cudaMemcpyHostToDevice, s), "H2D B"))
     return RTAT_B200_STATUS_EXECUTION_FAILED;
-  if (*beta != T(0) &&
-      cudaMemcpyAsync(dC, C, sizeof(T) * size_t(ldc) * n, cudaMemcpyHostToDevice, s) != cudaSuccess)
+  if (*beta != T(0) && !cuda_ok(cudaMemcpyAsync(dC, C, sizeof(T) * size_t(ldc) * n, cudaMemcpyHostToDevice, s), "H2D C"))
     return RTAT_B200_STATUS_EXECUTION_FAILED;
   st = gemm_fn(h, transa, transb, m, n, k, *alpha, dA, lda, dB, ldb, *beta, dC, ldc);
   if (st) return st;
   // copy back only the m x n window (ldc padding rows on the host are left untouched)
-  if (cudaMemcpy2DAsync(C, sizeof(T) * ldc, dC, sizeof(T) * ldc, sizeof(T) * m, n,
-                        cudaMemcpyDeviceToHost, s) != cudaSuccess)
+  if (!cuda_ok(cudaMemcpy2DAsync(C, sizeof(T) * ldc, dC, sizeof(T) * ldc, sizeof(T) * m, n, cudaMemcpyDeviceToHost, s), "D2H C"))
     return RTAT_B200_STATUS_EXECUTION_FAILED;
-  if (cudaStreamSynchronize(s) != cudaSuccess) return RTAT_B200_STATUS_EXECUTION_FAILED;
+  if (!cuda_ok(cudaStreamSynchronize(s), "synchronize")) return RTAT_B200_STATUS_EXECUTION_FAILED;
   return RTAT_B200_STATUS_SUCCESS;
 }
 

@@ -31,6 +31,13 @@ struct rtat_b200_context {
 
 namespace rtat_b200 {
 
+// cuTensorMapEncodeTiled resolved through the runtime, so the library has no link-time dependency
+// on libcuda (it must load, and fail cleanly in rtat_b200_create, on a box without a driver).
+typedef int (*tensor_map_encode_fn)(void *map, int dtype, unsigned rank, void *base, const unsigned long long *dims,
+                                    const unsigned long long *strides, const unsigned *box, const unsigned *estrides,
+                                    int interleave, int swizzle, int l2promo, int oobfill);
+void *tensor_map_encoder_raw();
+
 inline int opt(const rtat_b200_context *h, const char *key, int dflt = 0) {
   auto it = h->options.find(key);
   return it == h->options.end() ? dflt : it->second;

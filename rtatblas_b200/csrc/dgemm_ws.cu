@@ -421,13 +421,20 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_t tensor_map_encoder() { return reinterpret_cast<encode_tiled_t>(tensor_map_encoder_raw()); }
+
 static bool make_map(CUtensorMap *map, const double *base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems,
                      uint32_t box0, uint32_t box1) {
   cuuint64_t dims[2] = {dim0, dim1};
   cuuint64_t strides[1] = {ld_elems * sizeof(double)};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides,
+  auto encode = tensor_map_encoder();
+  if (!encode) return false;
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides,
                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;

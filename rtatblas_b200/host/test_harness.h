@@ -1,0 +1,173 @@
+// test_harness.h — JSON-driven benchmark harness (reference src/app/test_harness.h).
+// Input  {"keywords": {"run_type": "exhaustive"|"autotune", "method": "gemm"|"gemm_pad",
+//                      "data_type": "double"|"float", "repetitions": N [, "seed": S]},
+//         "problems": [ {"transA","transB","m","n","k"}, ... ]}
+// Output the same document with "problems" replaced by the planner statistics.
+// Differences from the reference: inputs come from a seeded generator and are generated once per
+// problem instead of before every repetition; "syrk"/"trsm" are rejected.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <rtat/gemm.h>
+#include <rtat/json_encoding.h>
+#include <rtat/planning_system.h>
+
+namespace rtat {
+
+struct Run_Type {
+  enum _Run_Type { EXHAUSTIVE, AUTOTUNE } val;
+  Run_Type(const std::string &s) {
+    if (s == "exhaustive") val = EXHAUSTIVE;
+    else if (s == "autotune") val = AUTOTUNE;
+    else throw std::runtime_error("Invalid run_type: " + s);
+  }
+  operator std::string() const { return val == EXHAUSTIVE ? "exhaustive" : "autotune"; }
+};
+
+struct Method {
+  enum _Method { GEMM, GEMM_PAD } val;
+  Method(const std::string &s) {
+    if (s == "gemm") val = GEMM;
+    else if (s == "gemm_pad") val = GEMM_PAD;
+    else if (s == "syrk" || s == "trsm") throw std::runtime_error("method " + s + " is outside the GEMM execution path this back end covers");
+    else throw std::runtime_error("Invalid method: " + s);
+  }
+  operator std::string() const { return val == GEMM ? "gemm" : "gemm_pad"; }
+};
+
+struct Data_Type {
+  enum _Data_Type { FLOAT, DOUBLE } val;
+  Data_Type(const std::string &s) {
+    if (s == "double") val = DOUBLE;
+    else if (s == "float") val = FLOAT;
+    else throw std::runtime_error("Invalid data_type: " + s);
+  }
+  operator std::string() const { return val == DOUBLE ? "double" : "float"; }
+};
+
+template <typename Key>
+class Problem_Set {
+  std::vector<Key> problems;
+
+ public:
+  explicit Problem_Set(const Json &list) {
+    for (auto &p : list.items()) problems.push_back(from_json<Key>(p));
+  }
+  const std::vector<Key> &get_problems() const { return problems; }
+};
+
+struct Input_File {
+  const Json problem_json;
+  const Run_Type run_type;
+  const Method method;
+  const Data_Type data_type;
+  const int repetitions;
+  const long long seed;
+  explicit Input_File(const Json &in)
+      : problem_json(in["problems"]),
+        run_type(in["keywords"]["run_type"].get<std::string>()),
+        method(in["keywords"]["method"].get<std::string>()),
+        data_type(in["keywords"]["data_type"].get<std::string>()),
+        repetitions(in["keywords"]["repetitions"].get<int>()),
+        seed(in["keywords"].contains("seed") ? in["keywords"]["seed"].get<long long>() : 0xB200) {}
+};
+
+// stream + handle + a grow-only input arena + a grow-only scratch arena
+struct Device_Resources {
+  Stream s;
+  gpu::blasHandle_t handle = nullptr;
+  ManagedWorkspace scratch_space;
+
+ private:
+  ManagedWorkspace space;
+  Device_RNG rng;
+
+ public:
+  explicit Device_Resources(uint64_t seed = 0xB200) : s(), scratch_space(1024), space(1024), rng(s, seed) {
+    blas_status_check(gpu::blasCreate(&handle), "blasCreate");
+    gpu::blasSetStream(handle, s);
+  }
+  ~Device_Resources() { gpu::blasDestroy(handle); }
+  void sync() { s.synchronize(); }
+
+  // carve 512-byte-aligned slices for the given shapes and fill them with U(0,1]
+  template <typename T>
+  std::vector<Matrix<T>> allocate_matrices(const std::vector<MatrixDims> &shapes) {
+    std::vector<size_t> elems;
+    size_t total = 0;
+    for (auto &d : shapes) {
+      size_t e = ((d.footprint() * sizeof(T) + 511) / 512) * 512 / sizeof(T);
+      elems.push_back(e);
+      total += e;
+    }
+    space.grow_to_fit<T>(total);
+    std::vector<Matrix<T>> out;
+    size_t offset = 0;
+    for (size_t i = 0; i < shapes.size(); i++) {
+      Workspace slice(space, offset, elems[i] * sizeof(T));
+      rng.uniform<T>((T *)slice, slice.size<T>());
+      out.emplace_back(slice, shapes[i]);
+      offset += elems[i] * sizeof(T);
+    }
+    return out;
+  }
+};
+
+template <typename Planner_Type>
+class Test_Harness {
+  using Params = typename Planner_Type::Params;
+  using Key = typename Planner_Type::Key;
+  using Opts = typename Planner_Type::Opts;
+  using Scalar = typename Params::Scalar;
+
+  Problem_Set<Key> problems;
+  Device_Resources resources;
+
+ public:
+  explicit Test_Harness(const Json &problem_json, uint64_t seed = 0xB200) : problems(problem_json), resources(seed) {}
+
+  // every problem x every plan x repetitions
+  Json run_exhaustive(int repetitions) {
+    Planner_Type planner;
+    for (auto &problem : problems.get_problems()) {
+      Params input = form_input<Scalar>(problem);
+      for (auto &opts : Opts::enumerate()) {
+        resources.scratch_space.template grow_to_fit<char>(planner.calculate_workspace(input, opts));
+        for (int i = 0; i < repetitions; i++) {
+          planner.execute(input, opts, resources.scratch_space, resources.s);
+          resources.sync();
+        }
+      }
+    }
+    return planner.make_statistics().json();
+  }
+
+  // what a user of the tuner sees: explore, converge, then keep running the winner
+  Json run_autotune(int repetitions) {
+    Planner_Type planner;
+    for (auto &problem : problems.get_problems()) {
+      Params input = form_input<Scalar>(problem);
+      for (int i = 0; i < repetitions; i++) {
+        auto opts = planner.create_plan(problem);
+        resources.scratch_space.template grow_to_fit<char>(planner.calculate_workspace(input, opts));
+        planner.execute(input, opts, resources.scratch_space, resources.s);
+        resources.sync();
+      }
+    }
+    return planner.make_statistics().json();
+  }
+
+  // tight leading dimensions, alpha = 1, beta = 0 (reference test_harness.h:232-248)
+  template <typename T>
+  GEMM_Inputs<T> form_input(GEMM_Key key) {
+    const bool an = key.transa == gpu::BLAS_OP_N, bn = key.transb == gpu::BLAS_OP_N;
+    MatrixDims Ad(an ? key.m : key.k, an ? key.k : key.m, an ? key.m : key.k);
+    MatrixDims Bd(bn ? key.k : key.n, bn ? key.n : key.k, bn ? key.k : key.n);
+    MatrixDims Cd(key.m, key.n, key.m);
+    auto ms = resources.allocate_matrices<T>({Ad, Bd, Cd});
+    return GEMM_Inputs<T>(resources.handle, key.transa, key.transb, ms[0], ms[1], ms[2], T(1), T(0));
+  }
+};
+
+}  // namespace rtat

@@ -272,3 +272,24 @@ def test_dgemm_config2_8192_tn(handle):
 def test_dgemm_config5_column_block(handle):
     # one GPU's share of config 5 at 8 GPUs, scaled to fit the test budget: m=k=8192, n=1024
     _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer entry points (what bench.py's e2e number times)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_host_entry(oracle, handle, dtype):
+    for (ta, tb, m, n, k, beta, pad) in [(1, 0, 300, 200, 100, 0.0, 0), (0, 1, 129, 65, 33, -0.5, 3), (0, 0, 1000, 900, 700, 0.0, 0)]:
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        lda, ldb, ldc = ar + pad, br + pad, m + pad
+        A, B, C0 = oracle.fill(lda * ac, 1, dtype), oracle.fill(ldb * bc, 2, dtype), oracle.fill(ldc * n, 3, dtype)
+        hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B)  # pinned and pageable
+        hC = torch.from_numpy(C0.copy())
+        for _ in range(2):  # second call reuses the staging arena
+            hC.copy_(torch.from_numpy(C0))
+            handle.gemm(dtype == np.float64, ta, tb, m, n, k, 1.0, hA, lda, hB, ldb, beta, hC, ldc, host=True)
+            got = hC.numpy()
+            ex, ab = oracle.gemm_exact(ta, tb, m, n, k, 1.0, A, lda, B, ldb, beta, C0, ldc)
+            assert np.all(np.abs(view(got, m, n, ldc).astype(np.float64) - ex) <= gemm_tolerance(dtype, k, ab, ex))
+            assert np.array_equal(view(got, ldc, n, ldc)[m:], view(C0, ldc, n, ldc)[m:])  # host padding rows untouched

@@ -26,8 +26,13 @@ int sgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, flo
   int variant = opt(h, "sgemm.variant");  // 0 auto, 1 = FP32 SIMT, 2 = tcgen05 3xTF32
   bool tc_ok = sgemm_tcgen05_supported(h, transa, transb, m, n, k, A, lda, B, ldb, C, ldc);
   if (variant == 2 && !tc_ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  if (variant == 2 || (variant == 0 && tc_ok))
-    return sgemm_tcgen05(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  // automatic choice: tensor cores whenever TMA can address the operands, except for problems so
+  // small that a single 128x128x32 tile pipeline is mostly padding
+  const bool worthwhile = (long long)m * n >= 64 * 64 && k >= 32;
+  if (variant == 2 || (variant == 0 && tc_ok && worthwhile)) {
+    int st = sgemm_tcgen05(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (st != RTAT_B200_STATUS_NOT_SUPPORTED || variant == 2) return st;
+  }
   return sgemm_simt(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 

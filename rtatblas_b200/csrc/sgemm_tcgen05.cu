@@ -1,9 +1,387 @@
-// placeholder until the tcgen05 3xTF32 kernel lands: reports "not supported" so the dispatcher
-// uses the FP32 kernel.
+// SGEMM on 5th-generation tensor cores with FP32-faithful accuracy (3xTF32):
+//     C = alpha * op(A) * op(B) + beta * C      (column-major)
+//
+// Replaces cublasSgemm (default math mode = true FP32) behind MatrixMult / MatrixMultAlloc for
+// T = float (reference src/matrix_ops/matrixop.h:33-42).  Each FP32 operand x is split into
+// big = tf32(x) and small = tf32(x - big); the product is accumulated in FP32 in tensor memory as
+// small*big + big*small + big*big, which recovers FP32-level accuracy (the dropped small*small
+// term and the rounding of the smalls are O(2^-22) relative).
+//
+// The tensor core adds into its FP32 accumulator with truncation, so a long accumulation chain at
+// full magnitude drifts by ~(k/8) half-ulps (measured: 3e-3 absolute at k = 4096, 12x an FP32 FMA
+// chain).  Two measures keep the result FP32-class: the cross terms (magnitude 2^-11 of the
+// product) get their own TMEM accumulator for the whole tile, and the big*big accumulator is
+// promoted every CHUNK_KB k-blocks (128 k): the epilogue warps drain it from TMEM and add it, with
+// round-to-nearest, into FP32 registers while the MMAs continue in the twin accumulator.
+//
+// Structure (one persistent CTA per SM, warp-specialised, everything synchronised by mbarriers):
+//   warp 0        TMA producer: raw FP32 tiles of op(A) (128 x 32) and op(B) (128 x 32) into a 3-stage
+//                 smem ring, 128 B swizzle.  Either stored orientation is loaded in place: a
+//                 K-contiguous operand is one {32 k} x {128 rows} box (K-major UMMA layout), an
+//                 M/N-contiguous operand four {32 mn} x {32 k} boxes (MN-major UMMA layout) — the
+//                 transpose is folded into the descriptors, never materialised.
+//   warps 4-7     split warps: turn each raw tile in place into its `big` part and write the `small`
+//                 part to a twin tile at the same (swizzled) offsets; fence to the async proxy.
+//   warp 1        MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per
+//                 k-block: big*big into one of two ping-pong 128-column TMEM accumulators (switched
+//                 every chunk), the two cross terms into a third; tcgen05.commit releases the smem
+//                 stage / publishes an accumulator.
+//   warps 8-11    epilogue: per chunk tcgen05.ld the finished big accumulator (each warp its own
+//                 32-lane quarter) and add it into 128 FP32 registers per thread; at the end of the
+//                 tile add the cross-term accumulator, apply alpha/beta, coalesced stores to C.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace rtat_b200 {
-bool sgemm_tcgen05_supported(const rtat_b200_context *, int, int, int, int, int, const float *, int,
-                             const float *, int, const float *, int) { return false; }
-int sgemm_tcgen05(rtat_b200_context *, int, int, int, int, int, float, const float *, int,
-                  const float *, int, float, float *, int) { return RTAT_B200_STATUS_NOT_SUPPORTED; }
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB: one operand tile (raw/big or small)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A, A_small, B, B_small
+constexpr int NUM_THREADS = 384;
+constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 8;
+constexpr int TMEM_COLS = 512;   // big ping, big pong, cross terms (3 x 128 columns; allocation is a power of two)
+constexpr int CHUNK_KB = 4;      // promote the big accumulator every 4 k-blocks = 128 k
+constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 + 256;
+
+struct Params {
+  int m, n, k;
+  float *C;
+  int ldc;
+  float alpha, beta;
+  int tiles_m, tiles_n, num_tiles, kb;  // kb = ceil(k / BK)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// ---- UMMA descriptors ------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128 B swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+// layout_type: 2 = SWIZZLE_128B (16 B chunks; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32 B chunks; the only
+// swizzled layout the tensor core accepts for MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)layout_type << 61);
+}
+// instruction descriptor for kind::tf32, FP32 accumulate: c_format=F32 [4,6) | a,b format TF32=2 [7,10),[10,13) |
+// a_major [15] | b_major [16] (1 = MN-major) | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_instr_desc(bool a_mn_major, bool b_mn_major, int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+// One operand's descriptor geometry.  KC: K contiguous in global => K-major tile [128 rows][32 k];
+// the four K=8 steps of a k-block advance the start address by 32 B inside the swizzle atom.
+// !KC: M/N contiguous => MN-major tile, four boxes [32 k][32 mn] 4 KB apart (LBO), loaded with TMA's
+// 128B_ATOM_32B swizzle: rows of 128 B per k, 32 B chunks XORed with (k & 3); the swizzle atom is 4 k-rows
+// (512 B = SBO), so a K=8 step is two atoms (1 KB).
+template <bool KC>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int kstep) {
+  if (KC) return make_smem_desc(tile_addr + kstep * 32, 16, 1024, 2);
+  return make_smem_desc(tile_addr + kstep * 1024, BK * 128, 512, 1);
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+  constexpr bool KCA = TA, KCB = !TB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier map (8 B each): full[s] | conv[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr slot
+  const uint32_t full0 = bar_base, conv0 = bar_base + 8 * STAGES, empty0 = bar_base + 16 * STAGES;
+  const uint32_t tfull0 = bar_base + 24 * STAGES, tempty0 = tfull0 + 16, sfull = tempty0 + 16, sempty = sfull + 8, tmem_slot = sempty + 8;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(conv0 + 8 * s, 4);   // one arrive per split warp
+      mbar_init(empty0 + 8 * s, 1);  // tcgen05.commit
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
+    }
+    mbar_init(sfull, 1);
+    mbar_init(sempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+        for (int kb = 0; kb < p.kb; kb++) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t full = full0 + 8 * stage;
+          const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + 2 * TILE_BYTES;
+          mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+          const int k0 = kb * BK;
+          if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
+          else
+            for (int b = 0; b < BM / 32; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 32 * b, k0, full);
+          if (KCB) tma_load_2d(sB, &mapB, k0, n0, full);
+          else
+            for (int b = 0; b < BN / 32; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 32 * b, k0, full);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_instr_desc(!KCA, !KCB, BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, small_phase = 0;
+      const uint32_t d_small = tmem_base + 2 * BN;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(sempty, small_phase ^ 1);  // epilogue has drained the cross-term accumulator of the previous tile
+        for (int kb = 0; kb < p.kb; kb++) {
+          const bool chunk_start = (kb % CHUNK_KB) == 0, chunk_end = ((kb + 1) % CHUNK_KB) == 0 || kb + 1 == p.kb;
+          if (chunk_start) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue has drained this big accumulator
+          mbar_wait(conv0 + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t d_big = tmem_base + acc * BN;
+          const uint32_t sA = smem_base + stage * STAGE_BYTES, sAs = sA + TILE_BYTES, sB = sA + 2 * TILE_BYTES, sBs = sA + 3 * TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ks++) {
+            const uint64_t a_big = operand_desc<KCA>(sA, ks), a_small = operand_desc<KCA>(sAs, ks);
+            const uint64_t b_big = operand_desc<KCB>(sB, ks), b_small = operand_desc<KCB>(sBs, ks);
+            umma_tf32(d_small, a_small, b_big, idesc, (kb | ks) != 0);
+            umma_tf32(d_small, a_big, b_small, idesc, 1);
+            umma_tf32(d_big, a_big, b_big, idesc, !(chunk_start && ks == 0));
+          }
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (chunk_end) {
+            umma_commit(tfull0 + 8 * acc);  // this chunk's big accumulator is complete
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+        umma_commit(sfull);  // cross terms complete
+        small_phase ^= 1;
+      }
+    }
+  } else if (warp >= SPLIT_WARP0 && warp < SPLIT_WARP0 + 4) {
+    // ===================== split warps: raw -> (big in place, small in the twin tile) =====================
+    const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.kb; kb++) {
+        mbar_wait(full0 + 8 * stage, phase);
+        const uint32_t sA = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; op++) {
+          const uint32_t raw = sA + op * 2 * TILE_BYTES, small = raw + TILE_BYTES;
+#pragma unroll
+          for (int c = 0; c < TILE_BYTES / 16 / 128; c++) {
+            const uint32_t off = (c * 128 + t) * 16;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw + off));
+            uint32_t b0 = to_tf32(v.x), b1 = to_tf32(v.y), b2 = to_tf32(v.z), b3 = to_tf32(v.w);
+            uint32_t s0 = to_tf32(v.x - __uint_as_float(b0)), s1 = to_tf32(v.y - __uint_as_float(b1));
+            uint32_t s2 = to_tf32(v.z - __uint_as_float(b2)), s3 = to_tf32(v.w - __uint_as_float(b3));
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(raw + off), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(small + off), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv0 + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int quarter = warp - EPI_WARP0;  // == warp % 4: the TMEM lanes this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0, small_phase = 0;
+    const float alpha = p.alpha, beta = p.beta;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    auto tmem_ld32 = [](uint32_t taddr, uint32_t (&r)[32]) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+      float sum[BN];  // this thread's row of the tile: FP32 registers, round-to-nearest adds
+#pragma unroll
+      for (int j = 0; j < BN; j++) sum[j] = 0.f;
+      const int chunks = (p.kb + CHUNK_KB - 1) / CHUNK_KB;
+      for (int ch = 0; ch < chunks; ch++) {
+        mbar_wait(tfull0 + 8 * acc, acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + acc * BN + c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; j++) sum[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      mbar_wait(sfull, small_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int row = m0 + quarter * 32 + lane;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + 2 * BN + c0, r);
+        if (row < p.m) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int col = n0 + c0 + j;
+            if (col < p.n) {
+              float *dst = p.C + (size_t)col * p.ldc + row;
+              float v = alpha * (sum[c0 + j] + __uint_as_float(r[j]));
+              if (beta != 0.f) v += beta * *dst;
+              *dst = v;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty);
+      small_phase ^= 1;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_map(CUtensorMap *map, const float *base, uint64_t dim0, uint64_t dim1, uint64_t ld_elems, uint32_t box0, uint32_t box1,
+                     CUtensorMapSwizzle swizzle) {
+  auto encode = reinterpret_cast<encode_tiled_t>(tensor_map_encoder_raw());
+  if (!encode) return false;
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool TA, bool TB>
+static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, const CUtensorMap &mb) {
+  auto kern = sgemm_tcgen05_kernel<TA, TB>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_INTERNAL_ERROR;
+    }
+    configured = true;
+  }
+  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, p);
+  return check_launch(h, "sgemm_tcgen05_3xtf32_128x128x32");
+}
+
+}  // namespace tc
+
+bool sgemm_tcgen05_supported(const rtat_b200_context *, int, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
+                             const float *, int) {
+  auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 4 == 0; };
+  return ok(A, lda) && ok(B, ldb) && m > 0 && n > 0 && k > 0;
+}
+
+int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha, const float *A, int lda, const float *B,
+                  int ldb, float beta, float *C, int ldc) {
+  using namespace tc;
+  const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
+  Params p{m, n, k, C, ldc, alpha, beta, 0, 0, 0, 0};
+  p.tiles_m = (m + BM - 1) / BM;
+  p.tiles_n = (n + BN - 1) / BN;
+  long long tiles = (long long)p.tiles_m * p.tiles_n;
+  if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  p.num_tiles = (int)tiles;
+  p.kb = (k + BK - 1) / BK;
+  CUtensorMap ma, mb;
+  // K-contiguous operand: dims {K, MN}, box {32, 128}; M/N-contiguous: dims {MN, K}, box {32, 32}
+  const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, mnmaj);
+  ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN, kmaj) : make_map(&mb, B, n, k, ldb, 32, BK, mnmaj));
+  if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  if (!ta && !tb) return launch<false, false>(h, p, ma, mb);
+  if (ta && !tb) return launch<true, false>(h, p, ma, mb);
+  if (!ta && tb) return launch<false, true>(h, p, ma, mb);
+  return launch<true, true>(h, p, ma, mb);
+}
+
+}  // namespace rtat_b200

@@ -293,3 +293,56 @@ def test_gemm_host_entry(oracle, handle, dtype):
             ex, ab = oracle.gemm_exact(ta, tb, m, n, k, 1.0, A, lda, B, ldb, beta, C0, ldc)
             assert np.all(np.abs(view(got, m, n, ldc).astype(np.float64) - ex) <= gemm_tolerance(dtype, k, ab, ex))
             assert np.array_equal(view(got, ldc, n, ldc)[m:], view(C0, ldc, n, ldc)[m:])  # host padding rows untouched
+
+
+# ---------------------------------------------------------------------------------------------
+# SGEMM on tcgen05 (3xTF32): forced with sgemm.variant = 2; needs 16 B aligned operands, ld % 4 == 0
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_sgemm_tcgen05_3xtf32(oracle, handle, ta, tb):
+    handle.set_option("sgemm.variant", 2)
+    try:
+        for (m, n, k) in [(128, 128, 32), (128, 128, 64), (256, 128, 96), (260, 132, 100), (64, 48, 40), (1, 1, 1), (513, 257, 33), (1024, 384, 520)]:
+            # leading dimensions rounded up to a multiple of 4 floats (what TMA can address)
+            ar = k if ta else m
+            br = n if tb else k
+            pad_a, pad_b = (-ar) % 4, (-br) % 4
+            err = _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.0, 0.0, 700 + m + k, lda_pad=pad_a, ldb_pad=pad_b)
+            assert handle.last_kernel().startswith("sgemm_tcgen05"), handle.last_kernel()
+            _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, -1.5, 0.75, 800 + m + k, lda_pad=pad_a + 4, ldb_pad=pad_b + 8, ldc_pad=3)
+            _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.0, 0.0, 900 + m + k, lda_pad=pad_a, ldb_pad=pad_b, nan_c=True)
+    finally:
+        handle.set_option("sgemm.variant", 0)
+
+
+def test_sgemm_tcgen05_rejects_what_tma_cannot_address(handle):
+    handle.set_option("sgemm.variant", 2)
+    try:
+        x = torch.zeros(70 * 70 + 8, dtype=torch.float32, device="cuda")
+        assert handle.gemm(False, 0, 0, 70, 45, 62, 1.0, x, 70, x, 62, 0.0, x, 70, check=False) == 15  # ld = 70: not a multiple of 4
+        assert handle.gemm(False, 0, 0, 64, 64, 64, 1.0, x.data_ptr() + 4, 64, x, 64, 0.0, x, 64, check=False) == 15  # 4 B aligned base
+    finally:
+        handle.set_option("sgemm.variant", 0)
+
+
+def test_sgemm_accuracy_is_fp32_class_not_tf32_class(oracle, handle):
+    """3xTF32 must be as accurate as an FP32 FMA chain: compare both against the exact product."""
+    m, n, k = 256, 128, 4096
+    A, B = oracle.fill(m * k, 11, np.float32), oracle.fill(k * n, 12, np.float32)
+    ex, ab = oracle.gemm_exact(0, 0, m, n, k, 1.0, A, m, B, k, 0.0, None, m)
+    errs = {}
+    for variant in (1, 2):
+        handle.set_option("sgemm.variant", variant)
+        dC = torch.empty(m * n, dtype=torch.float32, device="cuda")
+        handle.gemm(False, 0, 0, m, n, k, 1.0, dev(A), m, dev(B), k, 0.0, dC, m)
+        errs[variant] = np.abs(view(host(dC), m, n, m).astype(np.float64) - ex).max()
+    handle.set_option("sgemm.variant", 0)
+    scale = np.abs(ex).max()
+    assert errs[2] <= 4 * max(errs[1], 1e-7 * scale), errs      # same class as the FP32 kernel
+    assert errs[2] <= 2e-5 * scale, errs                         # a single-pass TF32 product would be ~1e-3
+
+
+def test_sgemm_config4_tall_skinny(handle):
+    # config 4: m=131072 n=128 k=4096 op NN (2.1 GB of A); checked against cuBLAS FP32 via torch
+    k = _full_size_vs_cublas(handle, np.float32, 0, 0, 131072, 128, 4096, 9004)
+    assert k.startswith("sgemm_tcgen05"), k

@@ -1,0 +1,55 @@
+/*
+ * rtat_b200_mg.h — column-split GEMM across the GPUs of one node (one process per GPU).
+ *
+ * The reference has no multi-GPU code; this layer is new and sits beside the
+ * single-GPU ABI of rtat_b200.h.  Scheme (BASELINE.json config 5): C's columns are split into
+ * contiguous blocks, rank r owns C[:, J_r] and op(B)[:, J_r] (zero-copy views in column-major
+ * storage), and A — which every rank needs in full — lives on a root rank and is replicated.
+ * No reduction is needed because K is not split.
+ *
+ * Replication is pipelined with the math: A is cut into K-panels; while the DMMA kernel multiplies
+ * panel p, the copy engines pull panel p+1 from the root's memory over NVLink (CUDA IPC peer
+ * mapping, no SMs used), so only the first panel's transfer is exposed.  The process group that
+ * exchanges the 64-byte IPC handle and provides barriers is the caller's (torch.distributed / NCCL
+ * in bench.py, gloo in the CPU tests); an NCCL broadcast of the panels is the alternative transport
+ * and is what bench.py falls back to when peer mapping is unavailable.
+ */
+#ifndef RTAT_B200_MG_H
+#define RTAT_B200_MG_H
+#include "rtat_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtat_b200_mg_context *rtat_b200_mg_t;
+#define RTAT_B200_MG_HANDLE_BYTES 64
+
+/* pure host helper: rank's contiguous column block [first, first + count) of n columns */
+int rtat_b200_mg_partition(int n, int world, int rank, int *first, int *count);
+/* pure host helper: K-panel p of `panels` over extent k: [first, first + count), multiples of 16 but the last */
+int rtat_b200_mg_panel(int k, int panels, int p, int *first, int *count);
+
+int rtat_b200_mg_create(rtat_b200_mg_t *mg, rtat_b200_handle_t handle, int rank, int world);
+int rtat_b200_mg_destroy(rtat_b200_mg_t mg);
+
+/* root: allocate `bytes` of device memory other processes can map; handle_out travels through the
+ * caller's process group */
+int rtat_b200_mg_alloc_shared(rtat_b200_mg_t mg, size_t bytes, void **dptr, unsigned char handle_out[RTAT_B200_MG_HANDLE_BYTES]);
+int rtat_b200_mg_free_shared(rtat_b200_mg_t mg, void *dptr);
+/* non-root: map the root's allocation into this process (peer access over NVLink) */
+int rtat_b200_mg_open_shared(rtat_b200_mg_t mg, const unsigned char handle[RTAT_B200_MG_HANDLE_BYTES], void **peer_dptr);
+int rtat_b200_mg_close_shared(rtat_b200_mg_t mg, void *peer_dptr);
+
+/* C_loc (m x n_loc) = alpha * op(A) * op(B_loc) + beta * C_loc.
+ * A_src: the full A — local memory on the root, the mapped peer pointer elsewhere.
+ * A_stage: local buffer with A's shape and leading dimension that receives the panels (may equal
+ * A_src, or be NULL, when A_src is local: then nothing is copied).
+ * panels: number of K-panels the transfer is pipelined over (>= 1).
+ * Work is enqueued on the handle's stream (math) and an internal copy stream; returns immediately. */
+int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A_src,
+                       int lda, double *A_stage, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc, int panels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

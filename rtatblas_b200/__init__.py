@@ -18,3 +18,5 @@ from ._capi import (  # noqa: F401
     exported_symbols,
 )
 from ._host import Planner, host_lib, host_lib_path  # noqa: F401
+from . import _mg as mg  # noqa: F401,E402
+from ._mg import ColumnSplit  # noqa: F401,E402

@@ -150,6 +150,10 @@ class Handle:
             _check(st, fn.__name__)
         return st
 
+    def fill_uniform_ptr(self, ptr, n, seed, lo=-1.0, hi=1.0, double=True):
+        fn = lib().rtat_b200_fill_uniform_d if double else lib().rtat_b200_fill_uniform_s
+        _check(fn(self._h, ptr, n, seed, lo, hi), "fill_uniform")
+
     def fill_uniform(self, x, seed, lo=-1.0, hi=1.0):
         import torch
 

@@ -8,7 +8,9 @@
 //   geam_stream_kernel : no operand transposed.  Each thread moves 16 B vectors (or scalars when an
 //                        operand's columns are not 16 B aligned, e.g. ld = 4097 doubles) for
 //                        several columns at once so that enough bytes are in flight per SM.
-//   geam_tile_kernel   : at least one operand transposed.  64x64 tiles are staged through padded
+//   geam_transpose_tma : (geam_tma.cu) A transposed, operands TMA-addressable: TMA load -> swizzled smem ->
+//                        conflict-free transposed smem-to-smem pass -> TMA store.
+//   geam_tile_kernel   : at least one operand transposed (any alignment).  64x64 tiles are staged through padded
 //                        shared memory (odd pitch => conflict-free transposed reads); global loads
 //                        run along the operand's contiguous dimension and global stores along C's.
 //
@@ -18,6 +20,11 @@
 #include "common.cuh"
 
 namespace rtat_b200 {
+
+template <typename T>
+bool geam_transpose_tma_supported(int m, int n, const T *A, int lda, const T *B, int ldb, const T *C, int ldc, bool use_b);
+template <typename T>
+int geam_transpose_tma(rtat_b200_context *h, int m, int n, T alpha, const T *A, int lda, T beta, const T *B, int ldb, T *C, int ldc);
 
 template <typename T>
 __device__ __forceinline__ T mul_rn(T a, T b);
@@ -76,7 +83,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
       for (int c = 0; c < COLS; c++) {
         int j = j0 + c;
         if (j < n) {
-          if (MODE != 1) va[c] = *reinterpret_cast<const V *>(A + (size_t)j * lda + i);
+          if (MODE != 1) va[c] = __ldcs(reinterpret_cast<const V *>(A + (size_t)j * lda + i));
           if (MODE != 0) vb[c] = *reinterpret_cast<const V *>(B + (size_t)j * ldb + i);
         }
       }
@@ -90,7 +97,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
           const T *pb = reinterpret_cast<const T *>(&vb[c]);
 #pragma unroll
           for (int e = 0; e < VN; e++) o[e] = axpby<T, MODE>(alpha, MODE != 1 ? pa[e] : T(0), beta, MODE != 0 ? pb[e] : T(0));
-          *reinterpret_cast<V *>(C + (size_t)j * ldc + i) = out;
+          __stcs(reinterpret_cast<V *>(C + (size_t)j * ldc + i), out);
         }
       }
     } else {
@@ -100,14 +107,14 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
       for (int c = 0; c < COLS; c++) {
         int j = j0 + c;
         if (j < n) {
-          if (MODE != 1) va[c] = A[(size_t)j * lda + i];
+          if (MODE != 1) va[c] = __ldcs(A + (size_t)j * lda + i);
           if (MODE != 0) vb[c] = B[(size_t)j * ldb + i];
         }
       }
 #pragma unroll
       for (int c = 0; c < COLS; c++) {
         int j = j0 + c;
-        if (j < n) C[(size_t)j * ldc + i] = axpby<T, MODE>(alpha, MODE != 1 ? va[c] : T(0), beta, MODE != 0 ? vb[c] : T(0));
+        if (j < n) __stcs(C + (size_t)j * ldc + i, axpby<T, MODE>(alpha, MODE != 1 ? va[c] : T(0), beta, MODE != 0 ? vb[c] : T(0)));
       }
     }
   }
@@ -198,6 +205,11 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
   int tiles_m = (m + TL - 1) / TL, tiles_n = (n + TL - 1) / TL;
   long long tiles = (long long)tiles_m * tiles_n;
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  if (ta && !tb && (MODE == 0 || MODE == 4) && opt(h, "geam.variant") != 1 &&
+      geam_transpose_tma_supported<T>(m, n, A, lda, B, ldb, C, ldc, MODE != 0)) {
+    int st = geam_transpose_tma<T>(h, m, n, alpha, A, lda, MODE == 0 ? T(0) : beta, B, ldb, C, ldc);
+    if (st != RTAT_B200_STATUS_NOT_SUPPORTED) return st;
+  }
   if (ta && !tb) {
     geam_tile_kernel<T, MODE, true, false, 64><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tiles_m, tiles_n);
     return check_launch(h, "geam_tile_tn");

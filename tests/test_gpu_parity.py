@@ -179,11 +179,30 @@ def test_geam_accumulate_and_general(oracle, handle, dtype):
         for ta in (0, 1):
             _geam_case(oracle, handle, dtype, ta, 0, 29, 18, 1.0, beta, 20, lda_pad=2, ldb_pad=1, ldc_pad=1, inplace=True)
             _geam_case(oracle, handle, dtype, ta, 0, 333, 129, 1.0, beta, 21, inplace=True)
+            _geam_case(oracle, handle, dtype, ta, 0, 520, 388, 1.0, beta, 22, inplace=True)          # TMA transpose(+accumulate) path
+            _geam_case(oracle, handle, dtype, ta, 0, 516, 260, -0.5, beta, 23, lda_pad=4, ldb_pad=8, ldc_pad=8, inplace=True)
     # all four op pairs out of place, general alpha/beta, alpha == 0
     for ta, tb in OPS:
         for alpha, beta in [(0.3, -1.7), (-2.0, 1.0), (0.0, 0.6), (1.0, 0.0)]:
             _geam_case(oracle, handle, dtype, ta, tb, 13, 7, alpha, beta, 30, lda_pad=1, ldb_pad=2, ldc_pad=3)
             _geam_case(oracle, handle, dtype, ta, tb, 150, 210, alpha, beta, 31)
+
+
+def test_geam_transpose_paths_agree_bitwise(oracle, handle):
+    """TMA transpose kernel vs the LSU tile kernel on a shape with ragged 64x64 edge tiles."""
+    for dtype in (np.float64, np.float32):
+        m, n = 1000, 1100
+        A = dev(oracle.fill(n * m, 5, dtype))
+        outs = []
+        for variant in (0, 1):
+            handle.set_option("geam.variant", variant)
+            Cm = torch.full((m * n,), float("nan"), dtype=torch.float64 if dtype == np.float64 else torch.float32, device="cuda")
+            handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, A, n, 0.0, Cm, m, Cm, m)
+            outs.append((host(Cm), handle.last_kernel()))
+        handle.set_option("geam.variant", 0)
+        assert outs[0][1].startswith("geam_transpose_tma") and outs[1][1].startswith("geam_tile")
+        assert np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8))
+        assert np.array_equal(outs[0][0].reshape(n, m), host(A).reshape(m, n).T)
 
 
 def test_geam_argument_checks(handle):
@@ -346,3 +365,29 @@ def test_sgemm_config4_tall_skinny(handle):
     # config 4: m=131072 n=128 k=4096 op NN (2.1 GB of A); checked against cuBLAS FP32 via torch
     k = _full_size_vs_cublas(handle, np.float32, 0, 0, 131072, 128, 4096, 9004)
     assert k.startswith("sgemm_tcgen05"), k
+
+
+def test_mg_panel_pipeline_on_one_gpu(oracle, handle):
+    """rtat_b200_mg_dgemm with a distinct stage buffer: the K-panel copy/GEMM pipeline (here a local
+    D2D copy stands in for the NVLink peer pull) must give the same C as one GEMM, for both op(A)."""
+    for ta, tb in ((0, 0), (1, 0), (0, 1)):
+        m, n, k = 300, 200, 530
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        lda = ar + 2
+        A, B, C0 = oracle.fill(lda * ac, 1), oracle.fill(br * bc, 2), oracle.fill(m * n, 3)
+        ex, ab = oracle.gemm_exact(ta, tb, m, n, k, 1.25, A, lda, B, br, -0.5, C0, m)
+        cs = rt.ColumnSplit(handle, 0, 1)
+        dA, dB = dev(A), dev(B)
+        for panels in (1, 5, 64):
+            stage = torch.full_like(dA, float("nan"))
+            for rep in range(2):  # second call reuses the stage: exercises the consumed-event handshake
+                dC = dev(C0)
+                cs.dgemm(ta, tb, m, n, k, 1.25, dA, lda, stage, dB, br, -0.5, dC, m, panels=panels)
+                got = host(dC)
+                assert np.all(np.abs(view(got, m, n, m) - ex) <= gemm_tolerance(np.float64, k, ab, ex)), (ta, tb, panels)
+        # root path: no stage, nothing copied
+        dC = dev(C0)
+        cs.dgemm(ta, tb, m, n, k, 1.25, dA, lda, None, dB, br, -0.5, dC, m)
+        assert np.all(np.abs(view(host(dC), m, n, m) - ex) <= gemm_tolerance(np.float64, k, ab, ex))
+        cs.close()

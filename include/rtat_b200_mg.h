@@ -29,6 +29,9 @@ int rtat_b200_mg_partition(int n, int world, int rank, int *first, int *count);
 /* pure host helper: K-panel p of `panels` over extent k: [first, first + count), multiples of 16 but the last */
 int rtat_b200_mg_panel(int k, int panels, int p, int *first, int *count);
 
+/* pure host helper: panel p (0..3) of the automatic schedule — 1/16, 3/16, 4/16, 8/16 of k */
+int rtat_b200_mg_auto_panel(int k, int p, int *first, int *count);
+
 int rtat_b200_mg_create(rtat_b200_mg_t *mg, rtat_b200_handle_t handle, int rank, int world);
 int rtat_b200_mg_destroy(rtat_b200_mg_t mg);
 
@@ -44,7 +47,8 @@ int rtat_b200_mg_close_shared(rtat_b200_mg_t mg, void *peer_dptr);
  * A_src: the full A — local memory on the root, the mapped peer pointer elsewhere.
  * A_stage: local buffer with A's shape and leading dimension that receives the panels (may equal
  * A_src, or be NULL, when A_src is local: then nothing is copied).
- * panels: number of K-panels the transfer is pipelined over (>= 1).
+ * panels: number of equal K-panels the transfer is pipelined over, or 0 for the automatic schedule
+ * (a small first panel, whose transfer is the only exposed one, then three growing ones).
  * Work is enqueued on the handle's stream (math) and an internal copy stream; returns immediately. */
 int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A_src,
                        int lda, double *A_stage, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc, int panels);

@@ -15,6 +15,7 @@ def _mg_lib():
         ip = C.POINTER(C.c_int)
         L.rtat_b200_mg_partition.argtypes = [i, i, i, ip, ip]
         L.rtat_b200_mg_panel.argtypes = [i, i, i, ip, ip]
+        L.rtat_b200_mg_auto_panel.argtypes = [i, i, ip, ip]
         L.rtat_b200_mg_create.argtypes = [C.POINTER(vp), vp, i, i]
         L.rtat_b200_mg_destroy.argtypes = [vp]
         L.rtat_b200_mg_alloc_shared.argtypes = [vp, sz, C.POINTER(vp), C.c_char_p]
@@ -38,6 +39,13 @@ def panel(k, panels, p):
     """K-panel p of `panels` over extent k: (first, count).  Pure host logic."""
     f, c = C.c_int(), C.c_int()
     _check(_mg_lib().rtat_b200_mg_panel(k, panels, p, C.byref(f), C.byref(c)), "rtat_b200_mg_panel")
+    return f.value, c.value
+
+
+def auto_panel(k, p):
+    """Panel p (0..3) of the automatic schedule: (first, count).  Pure host logic."""
+    f, c = C.c_int(), C.c_int()
+    _check(_mg_lib().rtat_b200_mg_auto_panel(k, p, C.byref(f), C.byref(c)), "rtat_b200_mg_auto_panel")
     return f.value, c.value
 
 
@@ -71,7 +79,7 @@ class ColumnSplit:
     def close_shared(self, ptr):
         _mg_lib().rtat_b200_mg_close_shared(self._mg, C.c_void_p(ptr))
 
-    def dgemm(self, transa, transb, m, n_loc, k, alpha, A_src, lda, A_stage, B_loc, ldb, beta, C_loc, ldc, panels=16):
+    def dgemm(self, transa, transb, m, n_loc, k, alpha, A_src, lda, A_stage, B_loc, ldb, beta, C_loc, ldc, panels=0):
         al, be = C.c_double(alpha), C.c_double(beta)
         _check(_mg_lib().rtat_b200_mg_dgemm(self._mg, transa, transb, m, n_loc, k, C.byref(al), _ptr(A_src), lda, _ptr(A_stage),
                                             _ptr(B_loc), ldb, C.byref(be), _ptr(C_loc), ldc, panels), "rtat_b200_mg_dgemm")

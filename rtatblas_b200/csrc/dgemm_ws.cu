@@ -496,7 +496,8 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
   p.sk_units = (long long)sk_tiles * p.kt;
   if (sk_tiles) {
     size_t slot_bytes = sizeof(double) * CONSUMER_WARPS * 32 * 64;
-    int st = ensure_arena(h, slot_bytes * grid);
+    // sized for a full-machine grid up front, so no call ever pays a reallocation (and its sync) later
+    int st = ensure_arena(h, slot_bytes * (grid > h->sm_count ? grid : h->sm_count));
     if (st) return st;
     if (!h->sk_flags) {
       if (cudaMalloc(&h->sk_flags, 4096) != cudaSuccess || cudaMemsetAsync(h->sk_flags, 0, 4096, h->stream) != cudaSuccess) {

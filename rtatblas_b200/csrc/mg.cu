@@ -46,6 +46,21 @@ int rtat_b200_mg_panel(int k, int panels, int p, int *first, int *count) {
   return RTAT_B200_STATUS_SUCCESS;
 }
 
+// Automatic schedule (panels == 0 in rtat_b200_mg_dgemm): four panels of 1/16, 3/16, 4/16 and 8/16 of K.
+// Only the first panel's transfer is exposed, so it is small; every further panel costs one extra
+// read-modify-write of C_loc (the panel GEMMs accumulate with beta = 1), so there are few of them.
+int rtat_b200_mg_auto_panel(int k, int p, int *first, int *count) {
+  if (k < 0 || p < 0 || p >= 4 || !first || !count) return RTAT_B200_STATUS_INVALID_VALUE;
+  static const int sixteenths[5] = {0, 1, 4, 8, 16};
+  auto cut = [&](int i) {
+    long long c = ((long long)k * sixteenths[i] / 16 + 15) / 16 * 16;
+    return (int)(c > k || i == 4 ? k : c);
+  };
+  *first = cut(p);
+  *count = cut(p + 1) - cut(p);
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
 int rtat_b200_mg_create(rtat_b200_mg_t *out, rtat_b200_handle_t handle, int rank, int world) {
   if (!out || !handle || world < 1 || rank < 0 || rank >= world) return RTAT_B200_STATUS_INVALID_VALUE;
   auto *mg = new rtat_b200_mg_context();
@@ -115,19 +130,23 @@ int rtat_b200_mg_close_shared(rtat_b200_mg_t mg, void *peer_dptr) {
 int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A_src,
                        int lda, double *A_stage, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc, int panels) {
   if (!mg || !alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
-  if (panels < 1) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (panels < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  const bool auto_schedule = panels == 0;
+  if (auto_schedule) panels = 4;
   rtat_b200_context *h = mg->h;
   const bool local = (A_stage == nullptr || A_stage == A_src);
   if (local || k == 0 || m == 0 || n_loc == 0)  // nothing to replicate: one GEMM on the resident operand
     return rtat_b200_dgemm(h, transa, transb, m, n_loc, k, alpha, A_src, lda, B_loc, ldb, beta, C_loc, ldc);
-  if (panels > (k + 15) / 16) panels = (k + 15) / 16;
+  if (!auto_schedule && panels > (k + 15) / 16) panels = (k + 15) / 16;
   ensure_events(mg, panels);
   const double one = 1.0;
   const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
+  bool first_gemm = true;
   for (int p = 0; p < panels; p++) {
     int k0, kw;
-    rtat_b200_mg_panel(k, panels, p, &k0, &kw);
-    if (kw <= 0) break;
+    if (auto_schedule) rtat_b200_mg_auto_panel(k, p, &k0, &kw);
+    else rtat_b200_mg_panel(k, panels, p, &k0, &kw);
+    if (kw <= 0) continue;
     // ---- copy engine: panel p of A, root -> local stage (waits until last call's GEMM has read the slot)
     if (mg->consumed_valid) cudaStreamWaitEvent(mg->copy_stream, mg->consumed[p], 0);
     cudaError_t e;
@@ -150,7 +169,8 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
     cudaStreamWaitEvent(h->stream, mg->landed[p], 0);
     const double *Ap = ta ? A_stage + k0 : A_stage + (size_t)k0 * lda;
     const double *Bp = tb ? B_loc + (size_t)k0 * ldb : B_loc + k0;
-    int st = rtat_b200_dgemm(h, transa, transb, m, n_loc, kw, alpha, Ap, lda, Bp, ldb, p == 0 ? beta : &one, C_loc, ldc);
+    int st = rtat_b200_dgemm(h, transa, transb, m, n_loc, kw, alpha, Ap, lda, Bp, ldb, first_gemm ? beta : &one, C_loc, ldc);
+    first_gemm = false;
     if (st) return st;
     cudaEventRecord(mg->consumed[p], h->stream);
   }

@@ -379,7 +379,7 @@ def test_mg_panel_pipeline_on_one_gpu(oracle, handle):
         ex, ab = oracle.gemm_exact(ta, tb, m, n, k, 1.25, A, lda, B, br, -0.5, C0, m)
         cs = rt.ColumnSplit(handle, 0, 1)
         dA, dB = dev(A), dev(B)
-        for panels in (1, 5, 64):
+        for panels in (0, 1, 5, 64):
             stage = torch.full_like(dA, float("nan"))
             for rep in range(2):  # second call reuses the stage: exercises the consumed-event handshake
                 dC = dev(C0)

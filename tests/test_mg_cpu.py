@@ -42,6 +42,13 @@ def test_panels_cover_k_in_order_and_respect_the_ktile():
                 pos = f + c
             assert pos == k
     assert rt.mg.panel(32768, 16, 5) == (5 * 2048, 2048)
+    # automatic schedule: 1/16, 3/16, 4/16, 8/16 of K, contiguous, k-tile aligned cuts
+    assert [rt.mg.auto_panel(32768, p) for p in range(4)] == [(0, 2048), (2048, 6144), (8192, 8192), (16384, 16384)]
+    for k in (1, 17, 100, 2049, 5000):
+        spans = [rt.mg.auto_panel(k, p) for p in range(4)]
+        assert spans[0][0] == 0 and spans[-1][0] + spans[-1][1] == k
+        for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+            assert f0 + c0 == f1 and c0 >= 0 and (f1 % 16 == 0 or f1 == k)
 
 
 WORKER = r'''

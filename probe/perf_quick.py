@@ -54,6 +54,18 @@ def geam_cfg(name, ta, m, n, ldc=None, dtype=torch.float64):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "tiles":
+    for t in (128, 64):
+        h.set_option("dgemm.tile", t)
+        print("tile", t)
+        dgemm_cfg("C1 dgemm NN 1024^3", 0, 0, 1024, 1024, 1024, variants=(3,))
+        dgemm_cfg("C2 dgemm TN 8192^3", 1, 0, 8192, 8192, 8192, variants=(3,))
+        dgemm_cfg("C3 dgemm NT 4097x3001x2049", 0, 1, 4097, 3001, 2049, variants=(3,))
+        dgemm_cfg("dgemm NN 2048^3", 0, 0, 2048, 2048, 2048, variants=(3,))
+        dgemm_cfg("dgemm NN 4096^3", 0, 0, 4096, 4096, 4096, variants=(3,))
+        dgemm_cfg("C5/8-like NN 8192x1024x8192", 0, 0, 8192, 1024, 8192, variants=(3,))
+        dgemm_cfg("dgemm NN 512^3", 0, 0, 512, 512, 512, variants=(3,))
+    h.set_option("dgemm.tile", 0)
 if which in ("all", "dgemm"):
     dgemm_cfg("C1 dgemm NN 1024^3", 0, 0, 1024, 1024, 1024)
     dgemm_cfg("C2 dgemm TN 8192^3", 1, 0, 8192, 8192, 8192, variants=(1, 3, 4))

@@ -219,7 +219,7 @@ static int launch_ops(rtat_b200_context *h, DgemmParams &p, int variant) {
 }
 
 int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
-             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma);
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg);
 
 int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, double alpha,
           const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc) {
@@ -249,8 +249,13 @@ int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, dou
     long long units = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16);
     variant = units >= 64 ? 3 : 2;
   }
-  if (variant == 3 || variant == 4)
-    return dgemm_ws(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, variant == 3 && !opt(h, "dgemm.force_unaligned"));
+  if (variant == 3 || variant == 4) {
+    bool tma = variant == 3 && !opt(h, "dgemm.force_unaligned");
+    int st = dgemm_ws(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tma, opt(h, "dgemm.tile"));  // dgemm.tile: 0 = choose, 64 / 128 = forced CTA tile
+    if (st == RTAT_B200_STATUS_NOT_SUPPORTED && tma)  // tensor map could not be encoded: same kernel, cp.async producers
+      st = dgemm_ws(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, opt(h, "dgemm.tile"));
+    return st;
+  }
 #define RTAT_DISPATCH(TA_, TB_)                                                            \
   (aligned ? launch_ops<TA_, TB_, true>(h, p, variant) : launch_ops<TA_, TB_, false>(h, p, variant))
   if (!ta && !tb) return RTAT_DISPATCH(false, false);

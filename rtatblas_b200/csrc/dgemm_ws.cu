@@ -33,13 +33,23 @@ namespace rtat_b200 {
 
 namespace ws {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 6;
-constexpr int WM = 64, WN = 32;                 // consumer warp tile
-constexpr int CONSUMER_WARPS = (BM / WM) * (BN / WN);  // 8
-constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BK = 16;
 constexpr int CPASYNC_PRODUCER_WARPS = 4;
-constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// CTA tile configuration.  Cfg128: 128x128 tiles, eight 64x32 consumer warps, one CTA per SM — the
+// steady-state workhorse (98 % DMMA pipe utilisation on 8192^3).  Cfg64: 64x64 tiles, four 32x32 consumer
+// warps, two CTAs per SM — four times smaller stream-K slots and finer edge granularity, for problems with
+// few or ragged tiles (1024^3; 4097 x 3001).
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int CTAS_PER_SM_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, CTAS_PER_SM = CTAS_PER_SM_;
+  static constexpr int CONSUMER_WARPS = (BM / WM) * (BN / WN);
+  static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLOT_DOUBLES = CONSUMER_WARPS * 32 * (WM / 8) * (WN / 8) * 2;
+  static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
+using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
 
 struct Params {
   int m, n, k;
@@ -188,17 +198,17 @@ struct FragAddr {
   }
 };
 
-// cp.async producer: one 128 x BK operand tile per call, 128 threads, 16 elements each.  Element
-// ownership is chosen so that everything but one add (and one xor for M/N-contiguous operands) per
-// element is loop-invariant: K-contiguous -> thread owns column kk = pt % 16 of rows pt/16 + 8i
-// (row & 7 is constant, so the swizzle term is too); M/N-contiguous -> thread owns element pt of k-row i.
-template <bool KC>
+// cp.async producer: one BMN x BK operand tile per call, 128 threads.  Element ownership is chosen so
+// that everything but one add (and one xor for M/N-contiguous operands) per element is loop-invariant:
+// K-contiguous -> thread owns column kk = pt % 16 of rows pt/16 + 8i (row & 7 is constant, so the swizzle
+// term is too); M/N-contiguous -> thread owns element pt % BMN of k-rows pt/BMN + (128/BMN) i.
+template <bool KC, int BMN>
 __device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *__restrict__ X, int ld, int mn0, int k0,
                                                       int MN, int K, int pt) {
   constexpr int PT = CPASYNC_PRODUCER_WARPS * 32;
-  constexpr int PER = 128 * BK / PT;
-  static_assert(PT == 128, "ownership pattern below assumes 128 producer threads");
+  static_assert(PT == 128 && PT % BMN == 0, "ownership pattern below assumes 128 producer threads");
   if (KC) {
+    constexpr int PER = BMN * BK / PT;
     const int kk = pt % BK, r0 = pt / BK;
     const bool kok = (k0 + kk) < K;
     const double *src0 = X + (size_t)(mn0 + r0) * ld + (k0 + kk);
@@ -210,21 +220,25 @@ __device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *
       cp_async8_zfill(dst0 + i * (PT / BK) * 128, ok ? src0 + i * step : X, ok ? 8 : 0);
     }
   } else {
-    const bool mok = (mn0 + pt) < MN;
-    const double *src0 = X + (size_t)k0 * ld + (mn0 + pt);
-    const uint32_t dst0 = s + (pt >> 4) * (BK * 128) + ((pt & 1) << 3);
-    const uint32_t c = (pt & 15) >> 1;
+    constexpr int KSTEP = PT / BMN, PER = BK / KSTEP;
+    const int mn = pt % BMN, kr0 = pt / BMN;
+    const bool mok = (mn0 + mn) < MN;
+    const double *src0 = X + (size_t)(k0 + kr0) * ld + (mn0 + mn);
+    const uint32_t dst0 = s + (mn >> 4) * (BK * 128) + ((mn & 1) << 3) + kr0 * 128;
+    const uint32_t c = (mn & 15) >> 1;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
-      bool ok = mok && (k0 + i) < K;
-      cp_async8_zfill(dst0 + i * 128 + ((c ^ (i & 7)) << 4), ok ? src0 + (size_t)i * ld : X, ok ? 8 : 0);
+      bool ok = mok && (k0 + kr0 + KSTEP * i) < K;
+      cp_async8_zfill(dst0 + i * KSTEP * 128 + ((c ^ ((kr0 + KSTEP * i) & 7)) << 4), ok ? src0 + (size_t)(KSTEP * i) * ld : X, ok ? 8 : 0);
     }
   }
 }
 
-template <bool TA, bool TB, bool USE_TMA>
-__global__ void __launch_bounds__((CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, 1)
+template <class Cfg, bool TA, bool TB, bool USE_TMA>
+__global__ void __launch_bounds__((Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, Cfg::CTAS_PER_SM)
 dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
+  constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr bool KCA = TA;    // op(A)(m,k): stored k x m when transposed => k contiguous
   constexpr bool KCB = !TB;   // op(B)(k,n): stored k x n when not transposed => k contiguous
   constexpr int PRODUCER_THREADS = USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS * 32;
@@ -295,8 +309,8 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int kt = seg.kb; kt < seg.ke; kt++) {
           mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
           uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + A_BYTES;
-          issue_operand_cpasync<KCA>(sA, p.A, p.lda, m0, kt * BK, p.m, p.k, pt);
-          issue_operand_cpasync<KCB>(sB, p.B, p.ldb, n0, kt * BK, p.n, p.k, pt);
+          issue_operand_cpasync<KCA, BM>(sA, p.A, p.lda, m0, kt * BK, p.m, p.k, pt);
+          issue_operand_cpasync<KCB, BN>(sB, p.B, p.ldb, n0, kt * BK, p.n, p.k, pt);
           cp_async_mbar_arrive_noinc(bar_base + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -322,7 +336,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   SegmentIter it(p, blockIdx.x, gridDim.x);
   Segment seg;
   const int ctid = threadIdx.x;  // 0..255 (consumer threads come first)
-  constexpr int SLOT_DOUBLES = CONSUMER_WARPS * 32 * MI * NI * 2;
+  constexpr int SLOT_DOUBLES = Cfg::SLOT_DOUBLES;
   while (it.next(seg)) {
     int m0, n0;
     tile_coords(seg.tile, m0, n0);
@@ -440,9 +454,11 @@ static bool make_map(CUtensorMap *map, const double *base, uint64_t dim0, uint64
   return r == CUDA_SUCCESS;
 }
 
-template <bool TA, bool TB, bool USE_TMA>
+template <class Cfg, bool TA, bool TB, bool USE_TMA>
 static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap &ma, const CUtensorMap &mb, const char *name) {
-  auto kern = dgemm_ws_kernel<TA, TB, USE_TMA>;
+  auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA>;
+  constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
+  constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
@@ -463,9 +479,39 @@ bool dgemm_ws_tma_ok(const double *A, int lda, const double *B, int ldb) {
   return ok(A, lda) && ok(B, ldb);
 }
 
-int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
-             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma) {
+// Stream-K finishers spin on flags raised by other CTAs, so every CTA of the grid must be resident at
+// once: never launch more CTAs than the occupancy calculator says fit.
+template <class Cfg, bool TA, bool TB, bool USE_TMA>
+static int resident_ctas_per_sm() {
+  static int cached = -1;
+  if (cached < 0) {
+    auto kern = ws::dgemm_ws_kernel<Cfg, TA, TB, USE_TMA>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    int occ = 0;
+    int threads = (Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : ws::CPASYNC_PRODUCER_WARPS)) * 32;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, Cfg::SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      occ = 1;
+    }
+    cached = occ < 1 ? 1 : (occ > Cfg::CTAS_PER_SM ? Cfg::CTAS_PER_SM : occ);
+  }
+  return cached;
+}
+template <class Cfg>
+static int resident_ctas_per_sm(bool ta, bool tb, bool tma) {
+#define RTAT_OCC(TA_, TB_) (tma ? resident_ctas_per_sm<Cfg, TA_, TB_, true>() : resident_ctas_per_sm<Cfg, TA_, TB_, false>())
+  if (!ta && !tb) return RTAT_OCC(false, false);
+  if (ta && !tb) return RTAT_OCC(true, false);
+  if (!ta && tb) return RTAT_OCC(false, true);
+  return RTAT_OCC(true, true);
+#undef RTAT_OCC
+}
+
+template <class Cfg>
+static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B,
+                   int ldb, double beta, double *C, int ldc, bool allow_tma, const char *tile_name) {
   using namespace ws;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN;
   Params p{};
   p.m = m; p.n = n; p.k = k;
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
@@ -477,10 +523,12 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
   p.num_tiles = (int)tiles;
   p.kt = (k + BK - 1) / BK;
   // ---- schedule: hybrid stream-K ---------------------------------------------------------------
-  // grid: one CTA per SM, fewer when there are not even MIN_UNITS k-tiles of work per CTA.
+  // grid: CTAS_PER_SM resident CTAs per SM, fewer when there are not even MIN_UNITS k-tiles of work per CTA.
   constexpr int MIN_UNITS = 4;
   long long units = tiles * p.kt;
-  int grid = h->sm_count;
+  bool use_tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
+  const int max_grid = h->sm_count * resident_ctas_per_sm<Cfg>(ta, tb, use_tma);
+  int grid = max_grid;
   if (units < (long long)grid * MIN_UNITS) grid = (int)((units + MIN_UNITS - 1) / MIN_UNITS);
   if (grid < 1) grid = 1;
   int sk_mode = opt(h, "dgemm.streamk", 1);  // 0 = data-parallel only (for A/B measurements)
@@ -495,9 +543,11 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
   p.dp_tiles = p.num_tiles - sk_tiles;
   p.sk_units = (long long)sk_tiles * p.kt;
   if (sk_tiles) {
-    size_t slot_bytes = sizeof(double) * CONSUMER_WARPS * 32 * 64;
-    // sized for a full-machine grid up front, so no call ever pays a reallocation (and its sync) later
-    int st = ensure_arena(h, slot_bytes * (grid > h->sm_count ? grid : h->sm_count));
+    // sized for the largest grid of either tile configuration up front, so no call ever pays a
+    // reallocation (and its sync) later
+    size_t arena = sizeof(double) * (size_t)Cfg128::SLOT_DOUBLES * h->sm_count * Cfg128::CTAS_PER_SM;
+    size_t arena64 = sizeof(double) * (size_t)Cfg64::SLOT_DOUBLES * h->sm_count * Cfg64::CTAS_PER_SM;
+    int st = ensure_arena(h, arena > arena64 ? arena : arena64);
     if (st) return st;
     if (!h->sk_flags) {
       if (cudaMalloc(&h->sk_flags, 4096) != cudaSuccess || cudaMemsetAsync(h->sk_flags, 0, 4096, h->stream) != cudaSuccess) {
@@ -510,23 +560,44 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
     p.sk_flags = static_cast<unsigned *>(h->sk_flags);
     p.sk_generation = ++h->sk_generation;
   }
-  bool use_tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof ma);
   memset(&mb, 0, sizeof mb);
   if (use_tma) {
     bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM) : make_map(&ma, A, m, k, lda, 16, BK);
     ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN) : make_map(&mb, B, n, k, ldb, 16, BK));
-    if (!ok) use_tma = false;  // e.g. strides beyond the descriptor's range: take the cp.async producers
+    if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;  // descriptor out of range (dims >= 2^32): caller falls back
   }
-#define RTAT_WS(TA_, TB_)                                                                                   \
-  (use_tma ? launch<TA_, TB_, true>(h, p, grid, ma, mb, sk_tiles ? "dgemm_ws_dmma_128x128x16_tma_streamk" : "dgemm_ws_dmma_128x128x16_tma") \
-           : launch<TA_, TB_, false>(h, p, grid, ma, mb, sk_tiles ? "dgemm_ws_dmma_128x128x16_cpasync8_streamk" : "dgemm_ws_dmma_128x128x16_cpasync8"))
+  // kernel name reported through rtat_b200_last_kernel: dgemm_ws_dmma_<tile>_{tma|cpasync8}[_streamk]
+  static thread_local char name[96];
+  snprintf(name, sizeof name, "dgemm_ws_dmma_%s_%s%s", tile_name, use_tma ? "tma" : "cpasync8", sk_tiles ? "_streamk" : "");
+#define RTAT_WS(TA_, TB_) \
+  (use_tma ? launch<Cfg, TA_, TB_, true>(h, p, grid, ma, mb, name) : launch<Cfg, TA_, TB_, false>(h, p, grid, ma, mb, name))
   if (!ta && !tb) return RTAT_WS(false, false);
   if (ta && !tb) return RTAT_WS(true, false);
   if (!ta && tb) return RTAT_WS(false, true);
   return RTAT_WS(true, true);
 #undef RTAT_WS
+}
+
+// tile_cfg: 0 = choose, 128 / 64 = forced
+int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg) {
+  if (tile_cfg == 0) {
+    // Estimated cost = padded tile area x waves.  128x128 tiles are the more efficient steady state
+    // (98 % vs ~94 % of the DMMA pipe), 64x64 tiles waste less on ragged edges and keep stream-K fix-ups
+    // four times smaller, which decides small problems.
+    auto padded = [&](int bm) { return (double)((m + bm - 1) / bm) * bm * (double)((n + bm - 1) / bm) * bm; };
+    // measured steady-state efficiencies: TMA producers 0.98 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
+    const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
+    double t128 = padded(128) / (tma ? 0.98 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
+    long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16);
+    bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
+    tile_cfg = (small || t64 < t128) ? 64 : 128;
+  }
+  if (tile_cfg == 64)
+    return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16");
+  return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16");
 }
 
 }  // namespace rtat_b200

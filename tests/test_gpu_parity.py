@@ -57,13 +57,15 @@ def test_dgemm_reference_test_shapes(oracle, handle, ta, tb, variant):
 
 
 @pytest.mark.parametrize("ta,tb", OPS)
-@pytest.mark.parametrize("variant", [0, 3])
-def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb, variant):
+@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (3, 64)])
+def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb, variant, tile):
     handle.set_option("dgemm.variant", variant)
+    handle.set_option("dgemm.tile", tile)
     try:
         _dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb)
     finally:
         handle.set_option("dgemm.variant", 0)
+        handle.set_option("dgemm.tile", 0)
 
 
 def _dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb):
@@ -114,10 +116,11 @@ def test_sgemm_reference_test_shapes(oracle, handle, ta, tb):
         _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.5, -0.5, 500 + m, lda_pad=1, ldb_pad=2, ldc_pad=3)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4])
-def test_dgemm_mid_size_against_oracle(oracle, handle, variant):
+@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (4, 128), (3, 64), (4, 64)])
+def test_dgemm_mid_size_against_oracle(oracle, handle, variant, tile):
     # large enough for many CTAs and k-tiles, small enough for the long-double oracle (~1 s)
     handle.set_option("dgemm.variant", variant)
+    handle.set_option("dgemm.tile", tile)
     try:
         _gemm_case(oracle, handle, np.float64, 1, 0, 512, 384, 640, 1.0, 0.0, 71)
         _gemm_case(oracle, handle, np.float64, 0, 1, 513, 383, 641, 1.0, 1.0, 73, lda_pad=1)
@@ -125,6 +128,7 @@ def test_dgemm_mid_size_against_oracle(oracle, handle, variant):
         _gemm_case(oracle, handle, np.float64, 1, 1, 2300, 1100, 200, -1.0, 0.5, 77, ldb_pad=2)
     finally:
         handle.set_option("dgemm.variant", 0)
+        handle.set_option("dgemm.tile", 0)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -92,7 +92,9 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   if (h->arena) cudaFree(h->arena);
   if (h->staging) cudaFree(h->staging);
   if (h->sk_flags) cudaFree(h->sk_flags);
-  if (h->staging_done) cudaEventDestroy(h->staging_done);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
+  for (auto e : h->host_events) if (e) cudaEventDestroy(e);
   delete h;
   return RTAT_B200_STATUS_SUCCESS;
 }
@@ -252,26 +254,61 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
     h->staging_bytes = need;
   }
   char *base = static_cast<char *>(h->staging);
-  T *dA = reinterpret_cast<T *>(base), *dB = reinterpret_cast<T *>(base + bytes_a),
-    *dC = reinterpret_cast<T *>(base + bytes_a + bytes_b);
-  cudaStream_t s = h->stream;
+  T *dA = reinterpret_cast<T *>(base), *dB = reinterpret_cast<T *>(base + bytes_a), *dC = reinterpret_cast<T *>(base + bytes_a + bytes_b);
   auto cuda_ok = [](cudaError_t e, const char *what) {
     if (e == cudaSuccess) return true;
     fprintf(stderr, "rtat_b200 host entry: %s: %s\n", what, cudaGetErrorString(e));
     (void)cudaGetLastError();
     return false;
   };
-  if (!cuda_ok(cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, s), "H2D A") ||
-      !cuda_ok(cudaMemcpyAsync(dB, B, sizeof(T) * ldb * cols_b, cudaMemcpyHostToDevice, s), "H2D B"))
+  // Lazily created side streams / events: H2D, math and D2H run as a column-block pipeline.
+  if (!h->copy_in) {
+    if (!cuda_ok(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking), "stream") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking), "stream"))
+      return RTAT_B200_STATUS_ALLOC_FAILED;
+    for (auto &e : h->host_events)
+      if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  cudaStream_t s = h->stream, sin = h->copy_in, sout = h->copy_out;
+  constexpr int MAX_BLOCKS = 8;
+  // column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128
+  int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
+  nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
+  const int blocks = (n + nb - 1) / nb;
+  cudaEvent_t *ev = h->host_events;  // [0] entry fence, [1] A landed, [2 + j] B_j landed, [10 + j] C_j computed
+  if (!cuda_ok(cudaEventRecord(ev[0], s), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+  cudaStreamWaitEvent(sin, ev[0], 0);
+  if (!cuda_ok(cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, sin), "H2D A")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+  cudaEventRecord(ev[1], sin);
+  cudaStreamWaitEvent(s, ev[1], 0);
+  for (int j = 0; j < blocks; j++) {
+    const int j0 = j * nb, cnt = (j0 + nb > n) ? n - j0 : nb;
+    // ---- H2D: columns [j0, j0 + cnt) of op(B) (and of C when beta != 0)
+    cudaError_t e;
+    if (transb == RTAT_B200_OP_N)
+      e = cudaMemcpyAsync(dB + (size_t)j0 * ldb, B + (size_t)j0 * ldb, sizeof(T) * (size_t)ldb * cnt, cudaMemcpyHostToDevice, sin);
+    else  // B is stored n x k: the block is rows [j0, j0 + cnt) of every column
+      e = cudaMemcpy2DAsync(dB + j0, sizeof(T) * ldb, B + j0, sizeof(T) * ldb, sizeof(T) * cnt, k, cudaMemcpyHostToDevice, sin);
+    if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    if (*beta != T(0) &&
+        !cuda_ok(cudaMemcpy2DAsync(dC + (size_t)j0 * ldc, sizeof(T) * ldc, C + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
+                                   cudaMemcpyHostToDevice, sin), "H2D C"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    cudaEventRecord(ev[2 + j], sin);
+    // ---- math on the handle's stream
+    cudaStreamWaitEvent(s, ev[2 + j], 0);
+    const T *Bj = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb : dB + j0;
+    st = gemm_fn(h, transa, transb, m, cnt, k, *alpha, dA, lda, Bj, ldb, *beta, dC + (size_t)j0 * ldc, ldc);
+    if (st) return st;
+    cudaEventRecord(ev[2 + MAX_BLOCKS + j], s);
+    // ---- D2H: only the m x cnt window (ldc padding rows on the host are left untouched)
+    cudaStreamWaitEvent(sout, ev[2 + MAX_BLOCKS + j], 0);
+    if (!cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
+                                   cudaMemcpyDeviceToHost, sout), "D2H C"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+  }
+  if (!cuda_ok(cudaStreamSynchronize(sout), "synchronize") || !cuda_ok(cudaStreamSynchronize(s), "synchronize"))
     return RTAT_B200_STATUS_EXECUTION_FAILED;
-  if (*beta != T(0) && !cuda_ok(cudaMemcpyAsync(dC, C, sizeof(T) * size_t(ldc) * n, cudaMemcpyHostToDevice, s), "H2D C"))
-    return RTAT_B200_STATUS_EXECUTION_FAILED;
-  st = gemm_fn(h, transa, transb, m, n, k, *alpha, dA, lda, dB, ldb, *beta, dC, ldc);
-  if (st) return st;
-  // copy back only the m x n window (ldc padding rows on the host are left untouched)
-  if (!cuda_ok(cudaMemcpy2DAsync(C, sizeof(T) * ldc, dC, sizeof(T) * ldc, sizeof(T) * m, n, cudaMemcpyDeviceToHost, s), "D2H C"))
-    return RTAT_B200_STATUS_EXECUTION_FAILED;
-  if (!cuda_ok(cudaStreamSynchronize(s), "synchronize")) return RTAT_B200_STATUS_EXECUTION_FAILED;
   return RTAT_B200_STATUS_SUCCESS;
 }
 

@@ -26,7 +26,8 @@ struct rtat_b200_context {
   // host-entry staging
   void *staging = nullptr;
   size_t staging_bytes = 0;
-  cudaEvent_t staging_done = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H side streams of the host entry points
+  cudaEvent_t host_events[2 + 2 * 8] = {};
 };
 
 namespace rtat_b200 {

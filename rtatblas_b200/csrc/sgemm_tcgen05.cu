@@ -9,26 +9,31 @@
 //
 // The tensor core adds into its FP32 accumulator with truncation, so a long accumulation chain at
 // full magnitude drifts by ~(k/8) half-ulps (measured: 3e-3 absolute at k = 4096, 12x an FP32 FMA
-// chain).  Two measures keep the result FP32-class: the cross terms (magnitude 2^-11 of the
-// product) get their own TMEM accumulator for the whole tile, and the big*big accumulator is
-// promoted every CHUNK_KB k-blocks (128 k): the epilogue warps drain it from TMEM and add it, with
-// round-to-nearest, into FP32 registers while the MMAs continue in the twin accumulator.
+// chain).  The accumulator is therefore promoted every CHUNK_KB k-blocks (128 k): the epilogue warps
+// drain it from TMEM and add it, with round-to-nearest, into FP32 registers while the MMAs continue
+// in the twin accumulator; inside a chunk the partial sums are small, and so are their ulps.
 //
 // Structure (one persistent CTA per SM, warp-specialised, everything synchronised by mbarriers):
-//   warp 0        TMA producer: raw FP32 tiles of op(A) (128 x 32) and op(B) (128 x 32) into a 3-stage
-//                 smem ring, 128 B swizzle.  Either stored orientation is loaded in place: a
-//                 K-contiguous operand is one {32 k} x {128 rows} box (K-major UMMA layout), an
-//                 M/N-contiguous operand four {32 mn} x {32 k} boxes (MN-major UMMA layout) — the
-//                 transpose is folded into the descriptors, never materialised.
-//   warps 4-7     split warps: turn each raw tile in place into its `big` part and write the `small`
-//                 part to a twin tile at the same (swizzled) offsets; fence to the async proxy.
-//   warp 1        MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per
-//                 k-block: big*big into one of two ping-pong 128-column TMEM accumulators (switched
-//                 every chunk), the two cross terms into a third; tcgen05.commit releases the smem
-//                 stage / publishes an accumulator.
-//   warps 8-11    epilogue: per chunk tcgen05.ld the finished big accumulator (each warp its own
-//                 32-lane quarter) and add it into 128 FP32 registers per thread; at the end of the
-//                 tile add the cross-term accumulator, apply alpha/beta, coalesced stores to C.
+//   warp 0        TMA producer: raw FP32 tiles of op(A) (128 x 32) and op(B) (128 x 32) into a 4-stage
+//                 smem ring.  Either stored orientation is loaded in place — the transpose is folded into
+//                 the descriptors, never materialised.
+//   warps 4-7     split warps.  A never goes back to shared memory: thread r reads row r of the A tile
+//                 (conflict-free either way: an M-contiguous tile is read one 128 B k-row per warp, a
+//                 K-contiguous tile through the 128 B swizzle), splits it in registers and tcgen05.st's
+//                 big and small straight into TENSOR MEMORY (lane r, 32 + 32 columns per stage), from
+//                 where the MMA takes its A operand.  B is split in shared memory: big in place, small
+//                 to a twin tile at the same (swizzled) offsets; fence to the async proxy.
+//   warp 1        MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8, A from
+//                 TMEM, B from smem: K-major SWIZZLE_128B or MN-major 128B_BASE32B) per k-block into one
+//                 of two ping-pong 128-column TMEM accumulators (switched every chunk); tcgen05.commit
+//                 releases the stage (smem + TMEM A slots) / publishes an accumulator.
+//   warps 8-11    epilogue: per chunk tcgen05.ld the finished accumulator (each warp its own 32-lane
+//                 quarter) and add it into 128 FP32 registers per thread; at the end of the tile apply
+//                 alpha/beta, coalesced stores to C.
+// Keeping A out of the MMA's shared-memory reads matters because this kernel is shared-memory-bandwidth
+// bound: per 32-k block the SM moves TMA 32 KB + split reads 32 KB + B split writes 32 KB + MMA B reads
+// 48 KB = 144 KB (the all-smem version moved 224 KB and reached 43 % tensor-pipe utilisation).
+// TMEM map (512 columns): [0,128) [128,256) accumulators; [256 + 64 s, +32) A_big, (+32, +64) A_small of stage s.
 #include <cuda.h>
 #include "common.cuh"
 
@@ -36,12 +41,13 @@ namespace rtat_b200 {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB: one operand tile (raw/big or small)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A, A_small, B, B_small
+constexpr int STAGES = 4;
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB: one operand tile
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;        // A raw, B raw -> big, B small
+constexpr int TMEM_A0 = 256;                       // first TMEM column of the A staging slots (64 per stage)
 constexpr int NUM_THREADS = 384;
 constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 8;
-constexpr int TMEM_COLS = 512;   // big ping, big pong, cross terms (3 x 128 columns; allocation is a power of two)
+constexpr int TMEM_COLS = 512;   // two accumulators + four A staging slots
 constexpr int CHUNK_KB = 4;      // promote the big accumulator every 4 k-blocks = 128 k
 constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 + 256;
 
@@ -108,6 +114,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row, one column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -132,7 +149,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
   // barrier map (8 B each): full[s] | conv[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr slot
   const uint32_t full0 = bar_base, conv0 = bar_base + 8 * STAGES, empty0 = bar_base + 16 * STAGES;
-  const uint32_t tfull0 = bar_base + 24 * STAGES, tempty0 = tfull0 + 16, sfull = tempty0 + 16, sempty = sfull + 8, tmem_slot = sempty + 8;
+  const uint32_t tfull0 = bar_base + 24 * STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   if (threadIdx.x == 0) {
@@ -145,8 +162,6 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
     }
-    mbar_init(sfull, 1);
-    mbar_init(sempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -169,7 +184,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int kb = 0; kb < p.kb; kb++) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t full = full0 + 8 * stage;
-          const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + 2 * TILE_BYTES;
+          const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + TILE_BYTES;
           mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
           const int k0 = kb * BK;
           if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
@@ -185,63 +200,100 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_instr_desc(!KCA, !KCB, BM, BN);
+      constexpr uint32_t idesc = make_instr_desc(false, !KCB, BM, BN);  // A comes from TMEM: always K-major
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, small_phase = 0;
-      const uint32_t d_small = tmem_base + 2 * BN;
+      uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(sempty, small_phase ^ 1);  // epilogue has drained the cross-term accumulator of the previous tile
         for (int kb = 0; kb < p.kb; kb++) {
           const bool chunk_start = (kb % CHUNK_KB) == 0, chunk_end = ((kb + 1) % CHUNK_KB) == 0 || kb + 1 == p.kb;
-          if (chunk_start) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue has drained this big accumulator
+          if (chunk_start) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
           mbar_wait(conv0 + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t d_big = tmem_base + acc * BN;
-          const uint32_t sA = smem_base + stage * STAGE_BYTES, sAs = sA + TILE_BYTES, sB = sA + 2 * TILE_BYTES, sBs = sA + 3 * TILE_BYTES;
+          const uint32_t d = tmem_base + acc * BN;
+          const uint32_t a_big_t = tmem_base + TMEM_A0 + 64 * stage, a_small_t = a_big_t + 32;
+          const uint32_t sB = smem_base + stage * STAGE_BYTES + TILE_BYTES, sBs = sB + TILE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ks++) {
-            const uint64_t a_big = operand_desc<KCA>(sA, ks), a_small = operand_desc<KCA>(sAs, ks);
             const uint64_t b_big = operand_desc<KCB>(sB, ks), b_small = operand_desc<KCB>(sBs, ks);
-            umma_tf32(d_small, a_small, b_big, idesc, (kb | ks) != 0);
-            umma_tf32(d_small, a_big, b_small, idesc, 1);
-            umma_tf32(d_big, a_big, b_big, idesc, !(chunk_start && ks == 0));
+            umma_tf32_ts(d, a_small_t + 8 * ks, b_big, idesc, !(chunk_start && ks == 0));
+            umma_tf32_ts(d, a_big_t + 8 * ks, b_small, idesc, 1);
+            umma_tf32_ts(d, a_big_t + 8 * ks, b_big, idesc, 1);
           }
-          umma_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage and its TMEM A slots once these MMAs have read them
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (chunk_end) {
-            umma_commit(tfull0 + 8 * acc);  // this chunk's big accumulator is complete
+            umma_commit(tfull0 + 8 * acc);  // this chunk's accumulator is complete
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           }
         }
-        umma_commit(sfull);  // cross terms complete
-        small_phase ^= 1;
       }
     }
   } else if (warp >= SPLIT_WARP0 && warp < SPLIT_WARP0 + 4) {
-    // ===================== split warps: raw -> (big in place, small in the twin tile) =====================
-    const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127
+    // ===================== split warps =====================
+    const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127 == row of the A tile == TMEM lane
+    const int quarter = warp - SPLIT_WARP0;        // == warp % 4: the TMEM lanes this warp may write
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.kb; kb++) {
         mbar_wait(full0 + 8 * stage, phase);
-        const uint32_t sA = smem_base + stage * STAGE_BYTES;
+        const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + TILE_BYTES, sBs = sB + TILE_BYTES;
+        // ---- A: row t of the raw tile -> registers -> big / small -> tensor memory
+        uint32_t big[32], small[32];
+        if (KCA) {
+          // K-major tile [128 rows][32 k], 16 B chunks XORed with (row & 7): 8 vector loads, conflict-free
 #pragma unroll
-        for (int op = 0; op < 2; op++) {
-          const uint32_t raw = sA + op * 2 * TILE_BYTES, small = raw + TILE_BYTES;
-#pragma unroll
-          for (int c = 0; c < TILE_BYTES / 16 / 128; c++) {
-            const uint32_t off = (c * 128 + t) * 16;
+          for (int c = 0; c < 8; c++) {
             float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw + off));
-            uint32_t b0 = to_tf32(v.x), b1 = to_tf32(v.y), b2 = to_tf32(v.z), b3 = to_tf32(v.w);
-            uint32_t s0 = to_tf32(v.x - __uint_as_float(b0)), s1 = to_tf32(v.y - __uint_as_float(b1));
-            uint32_t s2 = to_tf32(v.z - __uint_as_float(b2)), s3 = to_tf32(v.w - __uint_as_float(b3));
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(raw + off), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(small + off), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sA + t * 128 + ((c ^ (t & 7)) << 4)));
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              big[4 * c + e] = to_tf32(x[e]);
+              small[4 * c + e] = to_tf32(x[e] - __uint_as_float(big[4 * c + e]));
+            }
+          }
+        } else {
+          // M-major tile: box (t / 32) holds [32 k][32 m] unswizzled; a warp reads one 128 B k-row per load
+#pragma unroll
+          for (int kk = 0; kk < 32; kk++) {
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + (t >> 5) * (BK * 128) + kk * 128 + (t & 31) * 4));
+            big[kk] = to_tf32(x);
+            small[kk] = to_tf32(x - __uint_as_float(big[kk]));
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to UMMA
+        const uint32_t ta = lane_base + TMEM_A0 + 64 * stage;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(ta),
+            "r"(big[0]), "r"(big[1]), "r"(big[2]), "r"(big[3]), "r"(big[4]), "r"(big[5]), "r"(big[6]), "r"(big[7]), "r"(big[8]), "r"(big[9]),
+            "r"(big[10]), "r"(big[11]), "r"(big[12]), "r"(big[13]), "r"(big[14]), "r"(big[15]), "r"(big[16]), "r"(big[17]), "r"(big[18]),
+            "r"(big[19]), "r"(big[20]), "r"(big[21]), "r"(big[22]), "r"(big[23]), "r"(big[24]), "r"(big[25]), "r"(big[26]), "r"(big[27]),
+            "r"(big[28]), "r"(big[29]), "r"(big[30]), "r"(big[31])
+            : "memory");
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(ta + 32),
+            "r"(small[0]), "r"(small[1]), "r"(small[2]), "r"(small[3]), "r"(small[4]), "r"(small[5]), "r"(small[6]), "r"(small[7]), "r"(small[8]),
+            "r"(small[9]), "r"(small[10]), "r"(small[11]), "r"(small[12]), "r"(small[13]), "r"(small[14]), "r"(small[15]), "r"(small[16]),
+            "r"(small[17]), "r"(small[18]), "r"(small[19]), "r"(small[20]), "r"(small[21]), "r"(small[22]), "r"(small[23]), "r"(small[24]),
+            "r"(small[25]), "r"(small[26]), "r"(small[27]), "r"(small[28]), "r"(small[29]), "r"(small[30]), "r"(small[31])
+            : "memory");
+        // ---- B: raw -> big in place, small to the twin tile (position-preserving, so layout-agnostic)
+#pragma unroll
+        for (int c = 0; c < TILE_BYTES / 16 / 128; c++) {
+          const uint32_t off = (c * 128 + t) * 16;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sB + off));
+          uint32_t b0 = to_tf32(v.x), b1 = to_tf32(v.y), b2 = to_tf32(v.z), b3 = to_tf32(v.w);
+          uint32_t s0 = to_tf32(v.x - __uint_as_float(b0)), s1 = to_tf32(v.y - __uint_as_float(b1));
+          uint32_t s2 = to_tf32(v.z - __uint_as_float(b2)), s3 = to_tf32(v.w - __uint_as_float(b3));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sB + off), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sBs + off), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");          // TMEM stores complete
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");          // generic-proxy smem writes -> visible to UMMA
         __syncwarp();
         if (lane == 0) mbar_arrive(conv0 + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -251,7 +303,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ===================== epilogue =====================
     const int quarter = warp - EPI_WARP0;  // == warp % 4: the TMEM lanes this warp may read
     int acc = 0;
-    uint32_t acc_phase = 0, small_phase = 0;
+    uint32_t acc_phase = 0;
     const float alpha = p.alpha, beta = p.beta;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     auto tmem_ld32 = [](uint32_t taddr, uint32_t (&r)[32]) {
@@ -285,30 +337,19 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      mbar_wait(sfull, small_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int row = m0 + quarter * 32 + lane;
+      if (row < p.m) {
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_base + 2 * BN + c0, r);
-        if (row < p.m) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int col = n0 + c0 + j;
-            if (col < p.n) {
-              float *dst = p.C + (size_t)col * p.ldc + row;
-              float v = alpha * (sum[c0 + j] + __uint_as_float(r[j]));
-              if (beta != 0.f) v += beta * *dst;
-              *dst = v;
-            }
+        for (int j = 0; j < BN; j++) {
+          const int col = n0 + j;
+          if (col < p.n) {
+            float *dst = p.C + (size_t)col * p.ldc + row;
+            float v = alpha * sum[j];
+            if (beta != 0.f) v += beta * *dst;
+            *dst = v;
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sempty);
-      small_phase ^= 1;
     }
   }
 
@@ -375,7 +416,8 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   CUtensorMap ma, mb;
   // K-contiguous operand: dims {K, MN}, box {32, 128}; M/N-contiguous: dims {MN, K}, box {32, 32}
   const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, mnmaj);
+  // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle
+  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
   ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN, kmaj) : make_map(&mb, B, n, k, ldb, 32, BK, mnmaj));
   if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
   if (!ta && !tb) return launch<false, false>(h, p, ma, mb);

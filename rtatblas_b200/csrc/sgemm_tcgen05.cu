@@ -35,6 +35,7 @@
 // 48 KB = 144 KB (the all-smem version moved 224 KB and reached 43 % tensor-pipe utilisation).
 // TMEM map (512 columns): [0,128) [128,256) accumulators; [256 + 64 s, +32) A_big, (+32, +64) A_small of stage s.
 #include <cuda.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace rtat_b200 {
@@ -140,9 +141,13 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int kstep) 
   return make_smem_desc(tile_addr + kstep * 1024, BK * 128, 512, 1);
 }
 
-template <bool TA, bool TB>
+// PRESPLIT: op(B) was split into big / small arrays in global memory by split_tf32_kernel (it is the
+// operand every M-tile re-reads, so splitting it once instead of once per tile takes the B work off
+// the split warps and 32 KB per k-block off the shared-memory pipe); mapB / mapBs address those arrays.
+template <bool TA, bool TB, bool PRESPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapBs, const Params p) {
   constexpr bool KCA = TA, KCB = !TB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -185,7 +190,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t full = full0 + 8 * stage;
           const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + TILE_BYTES;
-          mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+          mbar_arrive_expect_tx(full, (PRESPLIT ? 3 : 2) * TILE_BYTES);
           const int k0 = kb * BK;
           if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
           else
@@ -193,6 +198,12 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           if (KCB) tma_load_2d(sB, &mapB, k0, n0, full);
           else
             for (int b = 0; b < BN / 32; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 32 * b, k0, full);
+          if (PRESPLIT) {
+            const uint32_t sBs = sB + TILE_BYTES;
+            if (KCB) tma_load_2d(sBs, &mapBs, k0, n0, full);
+            else
+              for (int b = 0; b < BN / 32; b++) tma_load_2d(sBs + b * (BK * 128), &mapBs, n0 + 32 * b, k0, full);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -281,7 +292,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             : "memory");
         // ---- B: raw -> big in place, small to the twin tile (position-preserving, so layout-agnostic)
 #pragma unroll
-        for (int c = 0; c < TILE_BYTES / 16 / 128; c++) {
+        for (int c = 0; c < (PRESPLIT ? 0 : TILE_BYTES / 16 / 128); c++) {
           const uint32_t off = (c * 128 + t) * 16;
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sB + off));
@@ -293,7 +304,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");          // TMEM stores complete
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");          // generic-proxy smem writes -> visible to UMMA
+        if (!PRESPLIT) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy smem writes -> visible to UMMA
         __syncwarp();
         if (lane == 0) mbar_arrive(conv0 + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -378,9 +389,22 @@ static bool make_map(CUtensorMap *map, const float *base, uint64_t dim0, uint64_
                 swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool TA, bool TB>
-static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, const CUtensorMap &mb) {
-  auto kern = sgemm_tcgen05_kernel<TA, TB>;
+// B (rows x cols, leading dimension ldb) -> big = tf32(b), small = tf32(b - big), both with leading dimension ldo
+__global__ void split_tf32_kernel(const float *__restrict__ B, int ldb, int rows, int cols, float *__restrict__ big, float *__restrict__ small,
+                                  int ldo) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = int(i % rows), c = int(i / rows);
+    const float x = B[(size_t)c * ldb + r];
+    const uint32_t b = to_tf32(x);
+    big[(size_t)c * ldo + r] = __uint_as_float(b);
+    small[(size_t)c * ldo + r] = __uint_as_float(to_tf32(x - __uint_as_float(b)));
+  }
+}
+
+template <bool TA, bool TB, bool PRESPLIT>
+static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbs) {
+  auto kern = sgemm_tcgen05_kernel<TA, TB, PRESPLIT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
@@ -390,16 +414,29 @@ static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, 
     configured = true;
   }
   int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, p);
-  return check_launch(h, "sgemm_tcgen05_3xtf32_128x128x32");
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, mbs, p);
+  return check_launch(h, PRESPLIT ? "sgemm_tcgen05_3xtf32_128x128x32_presplitB" : "sgemm_tcgen05_3xtf32_128x128x32", PRESPLIT ? 2 : 1);
 }
 
 }  // namespace tc
 
-bool sgemm_tcgen05_supported(const rtat_b200_context *, int, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
+// op(B) is pre-split into the handle's arena when both halves fit in PRESPLIT_LIMIT bytes and B is re-read
+// by at least two M-tiles; B then needs no alignment at all (the pre-pass reads any ldb).
+constexpr size_t PRESPLIT_LIMIT = size_t(512) << 20;
+
+static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k) {
+  if (opt(h, "sgemm.presplit", 1) == 0) return false;
+  // either stored orientation of B: rows rounded up to 4 floats
+  const size_t bytes_n = 2 * sizeof(float) * ((size_t)(k + 3) / 4 * 4) * (size_t)n;  // stored k x n
+  const size_t bytes_t = 2 * sizeof(float) * ((size_t)(n + 3) / 4 * 4) * (size_t)k;  // stored n x k
+  return m > tc::BM && bytes_n <= PRESPLIT_LIMIT && bytes_t <= PRESPLIT_LIMIT;
+}
+
+bool sgemm_tcgen05_supported(const rtat_b200_context *h, int, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
                              const float *, int) {
   auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 4 == 0; };
-  return ok(A, lda) && ok(B, ldb) && m > 0 && n > 0 && k > 0;
+  if (!(m > 0 && n > 0 && k > 0) || !ok(A, lda)) return false;
+  return ok(B, ldb) || presplit_wanted(h, m, n, k);
 }
 
 int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha, const float *A, int lda, const float *B,
@@ -413,17 +450,38 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   p.num_tiles = (int)tiles;
   p.kb = (k + BK - 1) / BK;
-  CUtensorMap ma, mb;
+  const bool presplit = presplit_wanted(h, m, n, k);
+  const float *Bbig = B, *Bsmall = B;
+  int ldb_eff = ldb;
+  if (presplit) {
+    // stored B is (tb ? n x k : k x n); split copies keep that shape with a TMA-friendly leading dimension
+    const int rows = tb ? n : k, cols = tb ? k : n, ldo = (rows + 3) / 4 * 4;
+    const size_t half = sizeof(float) * (size_t)ldo * cols;
+    const size_t half_al = (half + 1023) & ~size_t(1023);
+    int st = ensure_arena(h, 2 * half_al);
+    if (st) return st;
+    float *big = static_cast<float *>(h->arena), *small = reinterpret_cast<float *>(static_cast<char *>(h->arena) + half_al);
+    long long total = (long long)rows * cols;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+    split_tf32_kernel<<<blocks, 256, 0, h->stream>>>(B, ldb, rows, cols, big, small, ldo);
+    Bbig = big;
+    Bsmall = small;
+    ldb_eff = ldo;
+  }
+  CUtensorMap ma, mb, mbs;
   // K-contiguous operand: dims {K, MN}, box {32, 128}; M/N-contiguous: dims {MN, K}, box {32, 32}
   const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle
   bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
-  ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN, kmaj) : make_map(&mb, B, n, k, ldb, 32, BK, mnmaj));
+  ok = ok && (!tb ? make_map(&mb, Bbig, k, n, ldb_eff, BK, BN, kmaj) : make_map(&mb, Bbig, n, k, ldb_eff, 32, BK, mnmaj));
+  ok = ok && (!tb ? make_map(&mbs, Bsmall, k, n, ldb_eff, BK, BN, kmaj) : make_map(&mbs, Bsmall, n, k, ldb_eff, 32, BK, mnmaj));
   if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  if (!ta && !tb) return launch<false, false>(h, p, ma, mb);
-  if (ta && !tb) return launch<true, false>(h, p, ma, mb);
-  if (!ta && tb) return launch<false, true>(h, p, ma, mb);
-  return launch<true, true>(h, p, ma, mb);
+#define RTAT_TC(TA_, TB_) (presplit ? launch<TA_, TB_, true>(h, p, ma, mb, mbs) : launch<TA_, TB_, false>(h, p, ma, mb, mbs))
+  if (!ta && !tb) return RTAT_TC(false, false);
+  if (ta && !tb) return RTAT_TC(true, false);
+  if (!ta && tb) return RTAT_TC(false, true);
+  return RTAT_TC(true, true);
+#undef RTAT_TC
 }
 
 }  // namespace rtat_b200

@@ -83,6 +83,13 @@ if which in ("all", "geam"):
     geam_cfg("transpose 4097x2049 ->ld2080", 1, 2049, 4097, 2080)
     geam_cfg("pad-copy 3001x2049 ->ld3008", 0, 3001, 2049, 3008)
     geam_cfg("transpose 131072x128 f32", 1, 128, 131072, dtype=torch.float32)
+if which == "sgemm_debug":
+    for dbg in (0, 1, 4, 5):
+        h.set_option("sgemm.debug", dbg)
+        print("debug", dbg)
+        dgemm_cfg("C4 sgemm NN 131072x128x4096", 0, 0, 131072, 128, 4096, variants=(2,), dtype=torch.float32)
+        dgemm_cfg("sgemm TN 4096^3", 1, 0, 4096, 4096, 4096, variants=(2,), dtype=torch.float32)
+    h.set_option("sgemm.debug", 0)
 if which in ("all", "sgemm"):
     dgemm_cfg("C4 sgemm NN 131072x128x4096", 0, 0, 131072, 128, 4096, variants=(1, 2), dtype=torch.float32)
     dgemm_cfg("sgemm NN 4096^3", 0, 0, 4096, 4096, 4096, variants=(1, 2), dtype=torch.float32)

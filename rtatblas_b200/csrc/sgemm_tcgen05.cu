@@ -13,28 +13,27 @@
 // drain it from TMEM and add it, with round-to-nearest, into FP32 registers while the MMAs continue
 // in the twin accumulator; inside a chunk the partial sums are small, and so are their ulps.
 //
-// Where the operands live
-//   op(B)  is the operand every M-tile re-reads, so it is split ONCE per call by split_tf32_kernel into
-//          big / small arrays in the handle's arena (N is processed in slabs when B is too large for
-//          that); the GEMM kernel TMA-loads both halves straight into UMMA layout (K-major:
-//          SWIZZLE_128B; N-major: TMA 128B_ATOM_32B + UMMA SWIZZLE_128B_BASE32B, the only MN-major
-//          layout tf32 accepts).  The pre-pass reads any ldb, so B needs no alignment.
-//   op(A)  is streamed once.  Its raw FP32 tiles land in a 4 x 16 KB shared-memory ring; thread r of
-//          the split warps reads row r of the tile (conflict-free either way: an M-contiguous tile is
-//          read one 128 B k-row per warp, a K-contiguous tile through the 128 B swizzle), splits it in
-//          registers and tcgen05.st's big and small into TENSOR MEMORY (lane r, 32 + 32 columns per
-//          slot).  The smem slot is released as soon as the row is in registers — not when the MMA is
-//          done — which is what keeps enough HBM requests in flight for the tall-skinny config 4.
-//          The MMA takes A from TMEM (TS mode), so A never costs shared-memory read bandwidth again.
-//
-// One persistent CTA per SM, warp-specialised, everything synchronised by mbarriers:
-//   warp 0 / 2    TMA producers (one thread each) for the A ring and the B ring
-//   warp 1        MMA issuer: 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per 32-k block into one of two
-//                 ping-pong 128-column TMEM accumulators; tcgen05.commit frees the TMEM A slot and the B stage
-//   warps 4-7     split warps (A: smem -> registers -> TMEM)
+// Structure (one persistent CTA per SM, warp-specialised, everything synchronised by mbarriers):
+//   warp 0        TMA producer: raw FP32 tiles of op(A) (128 x 32) and op(B) (128 x 32) into a 4-stage
+//                 smem ring.  Either stored orientation is loaded in place — the transpose is folded into
+//                 the descriptors, never materialised.
+//   warps 4-7     split warps.  A never goes back to shared memory: thread r reads row r of the A tile
+//                 (conflict-free either way: an M-contiguous tile is read one 128 B k-row per warp, a
+//                 K-contiguous tile through the 128 B swizzle), splits it in registers and tcgen05.st's
+//                 big and small straight into TENSOR MEMORY (lane r, 32 + 32 columns per stage), from
+//                 where the MMA takes its A operand.  B is split in shared memory: big in place, small
+//                 to a twin tile at the same (swizzled) offsets; fence to the async proxy.
+//   warp 1        MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8, A from
+//                 TMEM, B from smem: K-major SWIZZLE_128B or MN-major 128B_BASE32B) per k-block into one
+//                 of two ping-pong 128-column TMEM accumulators (switched every chunk); tcgen05.commit
+//                 releases the stage (smem + TMEM A slots) / publishes an accumulator.
 //   warps 8-11    epilogue: per chunk tcgen05.ld the finished accumulator (each warp its own 32-lane
-//                 quarter) into 128 FP32 registers per thread; at tile end alpha/beta and coalesced stores
-// TMEM map (512 columns): [0,128) [128,256) accumulators; [256 + 64 t, +32) A_big, (+32, +64) A_small of slot t.
+//                 quarter) and add it into 128 FP32 registers per thread; at the end of the tile apply
+//                 alpha/beta, coalesced stores to C.
+// Keeping A out of the MMA's shared-memory reads matters because this kernel is shared-memory-bandwidth
+// bound: per 32-k block the SM moves TMA 32 KB + split reads 32 KB + B split writes 32 KB + MMA B reads
+// 48 KB = 144 KB (the all-smem version moved 224 KB and reached 43 % tensor-pipe utilisation).
+// TMEM map (512 columns): [0,128) [128,256) accumulators; [256 + 64 s, +32) A_big, (+32, +64) A_small of stage s.
 #include <cuda.h>
 #include <algorithm>
 #include "common.cuh"
@@ -43,15 +42,15 @@ namespace rtat_b200 {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int A_STAGES = 4, B_STAGES = 5, T_SLOTS = 4;  // B is the latency-critical ring: a stage is only refilled after its MMAs complete
-constexpr int TILE_BYTES = BM * BK * 4;   // 16 KB: one operand tile
-constexpr int B_STAGE_BYTES = 2 * TILE_BYTES;  // big, small
-constexpr int TMEM_A0 = 256;              // first TMEM column of the A slots (64 per slot)
+constexpr int STAGES = 4;
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB: one operand tile
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;        // A raw, B raw -> big, B small
+constexpr int TMEM_A0 = 256;                       // first TMEM column of the A staging slots (64 per stage)
 constexpr int NUM_THREADS = 384;
 constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 8;
-constexpr int TMEM_COLS = 512;            // two accumulators + four A slots
-constexpr int CHUNK_KB = 4;               // promote the accumulator every 4 k-blocks = 128 k
-constexpr size_t SMEM_BYTES = size_t(A_STAGES) * TILE_BYTES + size_t(B_STAGES) * B_STAGE_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 512;   // two accumulators + four A staging slots
+constexpr int CHUNK_KB = 4;      // promote the big accumulator every 4 k-blocks = 128 k
+constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 + 256;
 
 struct Params {
   int m, n, k;
@@ -59,7 +58,6 @@ struct Params {
   int ldc;
   float alpha, beta;
   int tiles_m, tiles_n, num_tiles, kb;  // kb = ceil(k / BK)
-  int debug;  // profiling experiments only (sgemm.debug): 1 = issue big*big only, 4 = epilogue skips the chunk drains
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,8 +91,9 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 }
 
 // ---- UMMA descriptors ------------------------------------------------------------------------------
-// shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
-// layout [61,64): 2 = SWIZZLE_128B (16 B chunks; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32 B chunks; the only
+// shared-memory matrix descriptor, 128 B swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+// layout_type: 2 = SWIZZLE_128B (16 B chunks; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32 B chunks; the only
 // swizzled layout the tensor core accepts for MN-major 32-bit operands)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
@@ -105,6 +104,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 __host__ __device__ constexpr uint32_t make_instr_desc(bool a_mn_major, bool b_mn_major, int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // A operand from tensor memory (lane = row, one column per k), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -121,9 +130,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
 
-// B tile descriptor for K=8 step `kstep` of a 32-k block.  KC: K contiguous => K-major tile [128 rows][32 k]; a
-// step advances the start address by 32 B inside the swizzle atom.  !KC: N contiguous => four boxes [32 k][32 n]
-// 4 KB apart (LBO), rows of 128 B per k with 32 B chunks XORed by (k & 3); the swizzle atom is 4 k-rows
+// One operand's descriptor geometry.  KC: K contiguous in global => K-major tile [128 rows][32 k];
+// the four K=8 steps of a k-block advance the start address by 32 B inside the swizzle atom.
+// !KC: M/N contiguous => MN-major tile, four boxes [32 k][32 mn] 4 KB apart (LBO), loaded with TMA's
+// 128B_ATOM_32B swizzle: rows of 128 B per k, 32 B chunks XORed with (k & 3); the swizzle atom is 4 k-rows
 // (512 B = SBO), so a K=8 step is two atoms (1 KB).
 template <bool KC>
 __device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int kstep) {
@@ -131,26 +141,32 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int kstep) 
   return make_smem_desc(tile_addr + kstep * 1024, BK * 128, 512, 1);
 }
 
-template <bool TA, bool TB>
+// PRESPLIT: op(B) was split into big / small arrays in global memory by split_tf32_kernel (it is the
+// operand every M-tile re-reads, so splitting it once instead of once per tile takes the B work off
+// the split warps and 32 KB per k-block off the shared-memory pipe); mapB / mapBs address those arrays.
+template <bool TA, bool TB, bool PRESPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapBs, const Params p) {
   constexpr bool KCA = TA, KCB = !TB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_ring = smem_base, b_ring = smem_base + A_STAGES * TILE_BYTES, bar_base = b_ring + B_STAGES * B_STAGE_BYTES;
-  // barriers (8 B each)
-  const uint32_t a_full = bar_base, a_empty = a_full + 8 * A_STAGES;                // A smem ring: TMA -> split warps -> TMA
-  const uint32_t b_full = a_empty + 8 * A_STAGES, b_empty = b_full + 8 * B_STAGES;  // B smem ring: TMA -> MMA -> TMA
-  const uint32_t t_ready = b_empty + 8 * B_STAGES, t_free = t_ready + 8 * T_SLOTS;  // TMEM A slots: split -> MMA -> split
-  const uint32_t acc_full = t_free + 8 * T_SLOTS, acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier map (8 B each): full[s] | conv[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr slot
+  const uint32_t full0 = bar_base, conv0 = bar_base + 8 * STAGES, empty0 = bar_base + 16 * STAGES;
+  const uint32_t tfull0 = bar_base + 24 * STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < A_STAGES; s++) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 4); }
-    for (int s = 0; s < B_STAGES; s++) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < T_SLOTS; s++) { mbar_init(t_ready + 8 * s, 4); mbar_init(t_free + 8 * s, 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(acc_full + 8 * a, 1); mbar_init(acc_empty + 8 * a, 4); }
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(conv0 + 8 * s, 4);   // one arrive per split warp
+      mbar_init(empty0 + 8 * s, 1);  // tcgen05.commit
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -164,44 +180,31 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer: A ring =====================
+    // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.tiles_m) * BM;
+        const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
         for (int kb = 0; kb < p.kb; kb++) {
-          mbar_wait(a_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = a_full + 8 * stage, sA = a_ring + stage * TILE_BYTES;
-          mbar_arrive_expect_tx(full, TILE_BYTES);
-          if (KCA) tma_load_2d(sA, &mapA, kb * BK, m0, full);
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t full = full0 + 8 * stage;
+          const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + TILE_BYTES;
+          mbar_arrive_expect_tx(full, (PRESPLIT ? 3 : 2) * TILE_BYTES);
+          const int k0 = kb * BK;
+          if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
           else
-            for (int b = 0; b < BM / 32; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 32 * b, kb * BK, full);
-          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== TMA producer: B ring (pre-split big / small) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n0 = (tile / p.tiles_m) * BN;
-        for (int kb = 0; kb < p.kb; kb++) {
-          mbar_wait(b_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = b_full + 8 * stage, sB = b_ring + stage * B_STAGE_BYTES, sBs = sB + TILE_BYTES;
-          mbar_arrive_expect_tx(full, B_STAGE_BYTES);
-          if (KCB) {
-            tma_load_2d(sB, &mapB, kb * BK, n0, full);
-            tma_load_2d(sBs, &mapBs, kb * BK, n0, full);
-          } else {
-            for (int b = 0; b < BN / 32; b++) {
-              tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 32 * b, kb * BK, full);
-              tma_load_2d(sBs + b * (BK * 128), &mapBs, n0 + 32 * b, kb * BK, full);
-            }
+            for (int b = 0; b < BM / 32; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 32 * b, k0, full);
+          if (KCB) tma_load_2d(sB, &mapB, k0, n0, full);
+          else
+            for (int b = 0; b < BN / 32; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 32 * b, k0, full);
+          if (PRESPLIT) {
+            const uint32_t sBs = sB + TILE_BYTES;
+            if (KCB) tma_load_2d(sBs, &mapBs, k0, n0, full);
+            else
+              for (int b = 0; b < BN / 32; b++) tma_load_2d(sBs + b * (BK * 128), &mapBs, n0 + 32 * b, k0, full);
           }
-          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -209,79 +212,70 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_instr_desc(false, !KCB, BM, BN);  // A comes from TMEM: always K-major
-      int bs = 0, ts = 0, acc = 0;
-      uint32_t bphase = 0, tphase = 0, acc_phase = 0;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < p.kb; kb++) {
           const bool chunk_start = (kb % CHUNK_KB) == 0, chunk_end = ((kb + 1) % CHUNK_KB) == 0 || kb + 1 == p.kb;
-          if (chunk_start) mbar_wait(acc_empty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
-          mbar_wait(t_ready + 8 * ts, tphase);
-          mbar_wait(b_full + 8 * bs, bphase);
+          if (chunk_start) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          mbar_wait(conv0 + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t d = tmem_base + acc * BN;
-          const uint32_t a_big_t = tmem_base + TMEM_A0 + 64 * ts, a_small_t = a_big_t + 32;
-          const uint32_t sB = b_ring + bs * B_STAGE_BYTES, sBs = sB + TILE_BYTES;
+          const uint32_t a_big_t = tmem_base + TMEM_A0 + 64 * stage, a_small_t = a_big_t + 32;
+          const uint32_t sB = smem_base + stage * STAGE_BYTES + TILE_BYTES, sBs = sB + TILE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ks++) {
             const uint64_t b_big = operand_desc<KCB>(sB, ks), b_small = operand_desc<KCB>(sBs, ks);
-            if (!(p.debug & 1)) {
-              umma_tf32_ts(d, a_small_t + 8 * ks, b_big, idesc, !(chunk_start && ks == 0));
-              umma_tf32_ts(d, a_big_t + 8 * ks, b_small, idesc, 1);
-              umma_tf32_ts(d, a_big_t + 8 * ks, b_big, idesc, 1);
-            } else {
-              umma_tf32_ts(d, a_big_t + 8 * ks, b_big, idesc, !(chunk_start && ks == 0));
-            }
+            umma_tf32_ts(d, a_small_t + 8 * ks, b_big, idesc, !(chunk_start && ks == 0));
+            umma_tf32_ts(d, a_big_t + 8 * ks, b_small, idesc, 1);
+            umma_tf32_ts(d, a_big_t + 8 * ks, b_big, idesc, 1);
           }
-          umma_commit(t_free + 8 * ts);   // TMEM A slot reusable once these MMAs have read it
-          umma_commit(b_empty + 8 * bs);  // B stage reusable
-          if (++ts == T_SLOTS) { ts = 0; tphase ^= 1; }
-          if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage and its TMEM A slots once these MMAs have read them
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (chunk_end) {
-            umma_commit(acc_full + 8 * acc);  // this chunk's accumulator is complete
+            umma_commit(tfull0 + 8 * acc);  // this chunk's accumulator is complete
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           }
         }
       }
     }
   } else if (warp >= SPLIT_WARP0 && warp < SPLIT_WARP0 + 4) {
-    // ===================== split warps: A smem -> registers -> big / small -> tensor memory =====================
+    // ===================== split warps =====================
     const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127 == row of the A tile == TMEM lane
     const int quarter = warp - SPLIT_WARP0;        // == warp % 4: the TMEM lanes this warp may write
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    int as = 0, ts = 0;
-    uint32_t aphase = 0, tphase = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.kb; kb++) {
-        mbar_wait(a_full + 8 * as, aphase);
-        const uint32_t sA = a_ring + as * TILE_BYTES;
-        float x[32];
+        mbar_wait(full0 + 8 * stage, phase);
+        const uint32_t sA = smem_base + stage * STAGE_BYTES, sB = sA + TILE_BYTES, sBs = sB + TILE_BYTES;
+        // ---- A: row t of the raw tile -> registers -> big / small -> tensor memory
+        uint32_t big[32], small[32];
         if (KCA) {
           // K-major tile [128 rows][32 k], 16 B chunks XORed with (row & 7): 8 vector loads, conflict-free
 #pragma unroll
-          for (int c = 0; c < 8; c++)
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-                         : "=f"(x[4 * c]), "=f"(x[4 * c + 1]), "=f"(x[4 * c + 2]), "=f"(x[4 * c + 3])
-                         : "r"(sA + t * 128 + ((c ^ (t & 7)) << 4)));
+          for (int c = 0; c < 8; c++) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sA + t * 128 + ((c ^ (t & 7)) << 4)));
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              big[4 * c + e] = to_tf32(x[e]);
+              small[4 * c + e] = to_tf32(x[e] - __uint_as_float(big[4 * c + e]));
+            }
+          }
         } else {
           // M-major tile: box (t / 32) holds [32 k][32 m] unswizzled; a warp reads one 128 B k-row per load
 #pragma unroll
-          for (int kk = 0; kk < 32; kk++)
-            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x[kk]) : "r"(sA + (t >> 5) * (BK * 128) + kk * 128 + (t & 31) * 4));
+          for (int kk = 0; kk < 32; kk++) {
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + (t >> 5) * (BK * 128) + kk * 128 + (t & 31) * 4));
+            big[kk] = to_tf32(x);
+            small[kk] = to_tf32(x - __uint_as_float(big[kk]));
+          }
         }
-        uint32_t big[32], small[32];
-#pragma unroll
-        for (int kk = 0; kk < 32; kk++) {
-          big[kk] = to_tf32(x[kk]);
-          small[kk] = to_tf32(x[kk] - __uint_as_float(big[kk]));
-        }
-        // the row is in registers: hand the smem slot back to the TMA producer right away
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty + 8 * as);
-        if (++as == A_STAGES) { as = 0; aphase ^= 1; }
-
-        mbar_wait(t_free + 8 * ts, tphase ^ 1);  // the MMAs that read this TMEM slot last time have completed
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t ta = lane_base + TMEM_A0 + 64 * ts;
+        const uint32_t ta = lane_base + TMEM_A0 + 64 * stage;
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(ta),
             "r"(big[0]), "r"(big[1]), "r"(big[2]), "r"(big[3]), "r"(big[4]), "r"(big[5]), "r"(big[6]), "r"(big[7]), "r"(big[8]), "r"(big[9]),
@@ -296,11 +290,24 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             "r"(small[17]), "r"(small[18]), "r"(small[19]), "r"(small[20]), "r"(small[21]), "r"(small[22]), "r"(small[23]), "r"(small[24]),
             "r"(small[25]), "r"(small[26]), "r"(small[27]), "r"(small[28]), "r"(small[29]), "r"(small[30]), "r"(small[31])
             : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");  // TMEM stores complete
+        // ---- B: raw -> big in place, small to the twin tile (position-preserving, so layout-agnostic)
+#pragma unroll
+        for (int c = 0; c < (PRESPLIT ? 0 : TILE_BYTES / 16 / 128); c++) {
+          const uint32_t off = (c * 128 + t) * 16;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sB + off));
+          uint32_t b0 = to_tf32(v.x), b1 = to_tf32(v.y), b2 = to_tf32(v.z), b3 = to_tf32(v.w);
+          uint32_t s0 = to_tf32(v.x - __uint_as_float(b0)), s1 = to_tf32(v.y - __uint_as_float(b1));
+          uint32_t s2 = to_tf32(v.z - __uint_as_float(b2)), s3 = to_tf32(v.w - __uint_as_float(b3));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sB + off), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sBs + off), "r"(s0), "r"(s1), "r"(s2), "r"(s3) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");          // TMEM stores complete
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        if (!PRESPLIT) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy smem writes -> visible to UMMA
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_ready + 8 * ts);
-        if (++ts == T_SLOTS) { ts = 0; tphase ^= 1; }
+        if (lane == 0) mbar_arrive(conv0 + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -327,20 +334,18 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       for (int j = 0; j < BN; j++) sum[j] = 0.f;
       const int chunks = (p.kb + CHUNK_KB - 1) / CHUNK_KB;
       for (int ch = 0; ch < chunks; ch++) {
-        mbar_wait(acc_full + 8 * acc, acc_phase);
+        mbar_wait(tfull0 + 8 * acc, acc_phase);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        if (!(p.debug & 4) || ch + 1 == chunks) {
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + acc * BN + c0, r);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + acc * BN + c0, r);
 #pragma unroll
-            for (int j = 0; j < 32; j++) sum[c0 + j] += __uint_as_float(r[j]);
-          }
+          for (int j = 0; j < 32; j++) sum[c0 + j] += __uint_as_float(r[j]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + 8 * acc);
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       const int row = m0 + quarter * 32 + lane;
@@ -368,19 +373,6 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
 }
 
-// B (rows x cols, leading dimension ldb) -> big = tf32(b), small = tf32(b - big), both with leading dimension ldo
-__global__ void split_tf32_kernel(const float *__restrict__ B, int ldb, int rows, int cols, float *__restrict__ big, float *__restrict__ small,
-                                  int ldo) {
-  const long long total = (long long)rows * cols;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = int(i % rows), c = int(i / rows);
-    const float x = B[(size_t)c * ldb + r];
-    const uint32_t b = to_tf32(x);
-    big[(size_t)c * ldo + r] = __uint_as_float(b);
-    small[(size_t)c * ldo + r] = __uint_as_float(to_tf32(x - __uint_as_float(b)));
-  }
-}
-
 typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -397,9 +389,22 @@ static bool make_map(CUtensorMap *map, const float *base, uint64_t dim0, uint64_
                 swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool TA, bool TB>
+// B (rows x cols, leading dimension ldb) -> big = tf32(b), small = tf32(b - big), both with leading dimension ldo
+__global__ void split_tf32_kernel(const float *__restrict__ B, int ldb, int rows, int cols, float *__restrict__ big, float *__restrict__ small,
+                                  int ldo) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = int(i % rows), c = int(i / rows);
+    const float x = B[(size_t)c * ldb + r];
+    const uint32_t b = to_tf32(x);
+    big[(size_t)c * ldo + r] = __uint_as_float(b);
+    small[(size_t)c * ldo + r] = __uint_as_float(to_tf32(x - __uint_as_float(b)));
+  }
+}
+
+template <bool TA, bool TB, bool PRESPLIT>
 static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbs) {
-  auto kern = sgemm_tcgen05_kernel<TA, TB>;
+  auto kern = sgemm_tcgen05_kernel<TA, TB, PRESPLIT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
@@ -410,63 +415,73 @@ static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, 
   }
   int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, mbs, p);
-  return check_launch(h, "sgemm_tcgen05_3xtf32_128x128x32", 2);
+  return check_launch(h, PRESPLIT ? "sgemm_tcgen05_3xtf32_128x128x32_presplitB" : "sgemm_tcgen05_3xtf32_128x128x32", PRESPLIT ? 2 : 1);
 }
 
 }  // namespace tc
 
-// A must be TMA-addressable (16 B aligned base, ld % 4 == 0); B may be anything (the pre-pass reads it).
-bool sgemm_tcgen05_supported(const rtat_b200_context *, int, int, int m, int n, int k, const float *A, int lda, const float *, int,
+// op(B) is pre-split into the handle's arena when both halves fit in PRESPLIT_LIMIT bytes and B is re-read
+// by at least two M-tiles; B then needs no alignment at all (the pre-pass reads any ldb).
+constexpr size_t PRESPLIT_LIMIT = size_t(512) << 20;
+
+static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k) {
+  if (opt(h, "sgemm.presplit", 1) == 0) return false;
+  // either stored orientation of B: rows rounded up to 4 floats
+  const size_t bytes_n = 2 * sizeof(float) * ((size_t)(k + 3) / 4 * 4) * (size_t)n;  // stored k x n
+  const size_t bytes_t = 2 * sizeof(float) * ((size_t)(n + 3) / 4 * 4) * (size_t)k;  // stored n x k
+  return m > tc::BM && bytes_n <= PRESPLIT_LIMIT && bytes_t <= PRESPLIT_LIMIT;
+}
+
+bool sgemm_tcgen05_supported(const rtat_b200_context *h, int, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
                              const float *, int) {
-  return m > 0 && n > 0 && k > 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0 && lda % 4 == 0;
+  auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 4 == 0; };
+  if (!(m > 0 && n > 0 && k > 0) || !ok(A, lda)) return false;
+  return ok(B, ldb) || presplit_wanted(h, m, n, k);
 }
 
 int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha, const float *A, int lda, const float *B,
                   int ldb, float beta, float *C, int ldc) {
   using namespace tc;
   const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
-  // N is processed in slabs so that the split copy of op(B)'s slab (2 x k x slab floats) fits the arena budget
-  const size_t budget = size_t(opt(h, "sgemm.presplit_mb", 512)) << 20;
-  const size_t k4 = (size_t)(k + 3) / 4 * 4;
-  long long slab = (long long)(budget / (2 * sizeof(float) * k4));
-  slab = slab / BN * BN;
-  if (slab < BN) slab = BN;
-  if (slab > n) slab = n;
-  for (int j0 = 0; j0 < n; j0 += (int)slab) {
-    const int ns = (int)std::min<long long>(slab, n - j0);
-    // stored shape of the slab of B: not transposed -> k x ns at B + j0*ldb; transposed -> ns x k at B + j0
-    const float *Bs = tb ? B + j0 : B + (size_t)j0 * ldb;
-    const int rows = tb ? ns : k, cols = tb ? k : ns, ldo = (rows + 3) / 4 * 4;
-    const size_t half = ((sizeof(float) * (size_t)ldo * cols) + 1023) & ~size_t(1023);
-    int st = ensure_arena(h, 2 * half);
+  Params p{m, n, k, C, ldc, alpha, beta, 0, 0, 0, 0};
+  p.tiles_m = (m + BM - 1) / BM;
+  p.tiles_n = (n + BN - 1) / BN;
+  long long tiles = (long long)p.tiles_m * p.tiles_n;
+  if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  p.num_tiles = (int)tiles;
+  p.kb = (k + BK - 1) / BK;
+  const bool presplit = presplit_wanted(h, m, n, k);
+  const float *Bbig = B, *Bsmall = B;
+  int ldb_eff = ldb;
+  if (presplit) {
+    // stored B is (tb ? n x k : k x n); split copies keep that shape with a TMA-friendly leading dimension
+    const int rows = tb ? n : k, cols = tb ? k : n, ldo = (rows + 3) / 4 * 4;
+    const size_t half = sizeof(float) * (size_t)ldo * cols;
+    const size_t half_al = (half + 1023) & ~size_t(1023);
+    int st = ensure_arena(h, 2 * half_al);
     if (st) return st;
-    float *big = static_cast<float *>(h->arena), *small = reinterpret_cast<float *>(static_cast<char *>(h->arena) + half);
-    const long long total = (long long)rows * cols;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
-    split_tf32_kernel<<<blocks, 256, 0, h->stream>>>(Bs, ldb, rows, cols, big, small, ldo);
-
-    Params p{m, ns, k, C + (size_t)j0 * ldc, ldc, alpha, beta, 0, 0, 0, 0, opt(h, "sgemm.debug")};
-    p.tiles_m = (m + BM - 1) / BM;
-    p.tiles_n = (ns + BN - 1) / BN;
-    long long tiles = (long long)p.tiles_m * p.tiles_n;
-    if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
-    p.num_tiles = (int)tiles;
-    p.kb = (k + BK - 1) / BK;
-    CUtensorMap ma, mb, mbs;
-    // K-contiguous operand: dims {K, MN}, box {32, 128}; M/N-contiguous: dims {MN, K}, box {32, 32}.
-    // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle.
-    const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
-    ok = ok && (!tb ? make_map(&mb, big, k, ns, ldo, BK, BN, kmaj) : make_map(&mb, big, ns, k, ldo, 32, BK, mnmaj));
-    ok = ok && (!tb ? make_map(&mbs, small, k, ns, ldo, BK, BN, kmaj) : make_map(&mbs, small, ns, k, ldo, 32, BK, mnmaj));
-    if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
-    if (!ta && !tb) st = launch<false, false>(h, p, ma, mb, mbs);
-    else if (ta && !tb) st = launch<true, false>(h, p, ma, mb, mbs);
-    else if (!ta && tb) st = launch<false, true>(h, p, ma, mb, mbs);
-    else st = launch<true, true>(h, p, ma, mb, mbs);
-    if (st) return st;
+    float *big = static_cast<float *>(h->arena), *small = reinterpret_cast<float *>(static_cast<char *>(h->arena) + half_al);
+    long long total = (long long)rows * cols;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+    split_tf32_kernel<<<blocks, 256, 0, h->stream>>>(B, ldb, rows, cols, big, small, ldo);
+    Bbig = big;
+    Bsmall = small;
+    ldb_eff = ldo;
   }
-  return RTAT_B200_STATUS_SUCCESS;
+  CUtensorMap ma, mb, mbs;
+  // K-contiguous operand: dims {K, MN}, box {32, 128}; M/N-contiguous: dims {MN, K}, box {32, 32}
+  const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle
+  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+  ok = ok && (!tb ? make_map(&mb, Bbig, k, n, ldb_eff, BK, BN, kmaj) : make_map(&mb, Bbig, n, k, ldb_eff, 32, BK, mnmaj));
+  ok = ok && (!tb ? make_map(&mbs, Bsmall, k, n, ldb_eff, BK, BN, kmaj) : make_map(&mbs, Bsmall, n, k, ldb_eff, 32, BK, mnmaj));
+  if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
+#define RTAT_TC(TA_, TB_) (presplit ? launch<TA_, TB_, true>(h, p, ma, mb, mbs) : launch<TA_, TB_, false>(h, p, ma, mb, mbs))
+  if (!ta && !tb) return RTAT_TC(false, false);
+  if (ta && !tb) return RTAT_TC(true, false);
+  if (!ta && tb) return RTAT_TC(false, true);
+  return RTAT_TC(true, true);
+#undef RTAT_TC
 }
 
 }  // namespace rtat_b200

@@ -6,8 +6,8 @@
 // of every operand that is used and one write of C.
 //
 //   geam_stream_kernel : no operand transposed.  Each thread moves 16 B vectors (or scalars when an
-//                        operand's columns are not 16 B aligned, e.g. ld = 4097 doubles) for
-//                        several columns at once so that enough bytes are in flight per SM.
+//                        operand's columns are not 16 B aligned, e.g. ld = 4097 doubles), several
+//                        per thread in flight, the grid sweeping each column's chunks in memory order.
 //   geam_transpose_tma : (geam_tma.cu) A transposed, operands TMA-addressable: TMA load -> swizzled smem ->
 //                        conflict-free transposed smem-to-smem pass -> TMA store.
 //   geam_tile_kernel   : at least one operand transposed (any alignment).  64x64 tiles are staged through padded
@@ -17,6 +17,7 @@
 // Arithmetic (pinned bit-for-bit against cuBLAS 12.9 geam through tests/golden): beta == 0 =>
 // c = alpha*a with B never read; alpha == 0 => c = beta*b with A never read; otherwise
 // c = fma(beta, b, RN(alpha*a)).
+#include <type_traits>
 #include "common.cuh"
 
 namespace rtat_b200 {
@@ -62,59 +63,125 @@ struct Vec16<double> { using type = double2; static constexpr int N = 2; };
 template <>
 struct Vec16<float> { using type = float4; static constexpr int N = 4; };
 
-// ---------------------------------------------------------------------------------------------
-// streaming kernel (no transposes).  A tile is ROWS_PER_CTA rows x COLS columns.
-// ---------------------------------------------------------------------------------------------
-template <typename T, int MODE, bool VEC, int COLS>
+// 256-bit global accesses (LDG.E.256 / STG.E.256, new on sm_100): 4 doubles or 8 floats per instruction
+template <typename T>
+struct Vec32;
+template <>
+struct Vec32<double> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(double (&v)[4], const double *p) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  }
+  static __device__ __forceinline__ void store(double *p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  }
+};
+template <>
+struct Vec32<float> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(float (&v)[8], const float *p) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+  }
+  static __device__ __forceinline__ void store(float *p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  }
+};
+
+// streaming kernel on 32 B vectors (every operand 32 B aligned, ld and m multiples of 32 B): same chunk
+// walk as geam_stream_kernel below
+template <typename T, int MODE, int UNR>
 __global__ void __launch_bounds__(256)
-geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B,
-                   int ldb, T *C, int ldc, int row_tiles) {
-  constexpr int VN = VEC ? Vec16<T>::N : 1;
-  constexpr int ROWS = 256 * VN;
-  using V = typename Vec16<T>::type;
-  for (long long tile = blockIdx.x; tile < (long long)row_tiles * ((n + COLS - 1) / COLS); tile += gridDim.x) {
-    int rt = int(tile % row_tiles), ct = int(tile / row_tiles);
-    int i = rt * ROWS + threadIdx.x * VN;
-    int j0 = ct * COLS;
-    if (VEC) {
-      if (i >= m) continue;  // m % VN == 0 is guaranteed by the dispatcher for the vector path
-      V va[COLS], vb[COLS];
+geam_stream256_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb, T *C, int ldc,
+                      int chunks_per_col) {
+  constexpr int VN = Vec32<T>::N;
+  constexpr int CHUNK = 256 * VN * UNR;
+  const long long total = (long long)chunks_per_col * n;
+  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+    const int j = int(w / chunks_per_col);
+    const int i0 = int(w % chunks_per_col) * CHUNK + threadIdx.x * VN;
+    const T *a = A + (size_t)j * lda, *b = B + (size_t)j * ldb;
+    T *c = C + (size_t)j * ldc;
+    T va[UNR][VN], vb[UNR][VN];
 #pragma unroll
-      for (int c = 0; c < COLS; c++) {
-        int j = j0 + c;
-        if (j < n) {
-          if (MODE != 1) va[c] = __ldcs(reinterpret_cast<const V *>(A + (size_t)j * lda + i));
-          if (MODE != 0) vb[c] = *reinterpret_cast<const V *>(B + (size_t)j * ldb + i);
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u * 256 * VN;
+      if (i < m) {
+        if (MODE != 1) Vec32<T>::load(va[u], a + i);
+        if (MODE != 0) Vec32<T>::load(vb[u], b + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u * 256 * VN;
+      if (i < m) {
+        T out[VN];
+#pragma unroll
+        for (int e = 0; e < VN; e++) out[e] = axpby<T, MODE>(alpha, MODE != 1 ? va[u][e] : T(0), beta, MODE != 0 ? vb[u][e] : T(0));
+        Vec32<T>::store(c + i, out);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming kernel (no transposes).  Work item = one chunk of 256*VN*UNR consecutive elements of one
+// column; consecutive CTAs take consecutive chunks, so for tight leading dimensions the whole grid
+// sweeps memory linearly (DRAM-page friendly), and every thread keeps UNR 16 B requests in flight.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool VEC, int UNR>
+__global__ void __launch_bounds__(256)
+geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb, T *C, int ldc,
+                   int chunks_per_col) {
+  constexpr int VN = VEC ? Vec16<T>::N : 1;
+  constexpr int CHUNK = 256 * VN * UNR;
+  using V = typename Vec16<T>::type;
+  const long long total = (long long)chunks_per_col * n;
+  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+    const int j = int(w / chunks_per_col);
+    const int i0 = int(w % chunks_per_col) * CHUNK + threadIdx.x * VN;
+    const T *a = A + (size_t)j * lda, *b = B + (size_t)j * ldb;
+    T *c = C + (size_t)j * ldc;
+    if (VEC) {
+      V va[UNR], vb[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const int i = i0 + u * 256 * VN;
+        if (i < m) {  // m % VN == 0 is guaranteed by the dispatcher for the vector path
+          if (MODE != 1) va[u] = __ldcs(reinterpret_cast<const V *>(a + i));
+          if (MODE != 0) vb[u] = *reinterpret_cast<const V *>(b + i);
         }
       }
 #pragma unroll
-      for (int c = 0; c < COLS; c++) {
-        int j = j0 + c;
-        if (j < n) {
+      for (int u = 0; u < UNR; u++) {
+        const int i = i0 + u * 256 * VN;
+        if (i < m) {
           V out;
           T *o = reinterpret_cast<T *>(&out);
-          const T *pa = reinterpret_cast<const T *>(&va[c]);
-          const T *pb = reinterpret_cast<const T *>(&vb[c]);
+          const T *pa = reinterpret_cast<const T *>(&va[u]);
+          const T *pb = reinterpret_cast<const T *>(&vb[u]);
 #pragma unroll
           for (int e = 0; e < VN; e++) o[e] = axpby<T, MODE>(alpha, MODE != 1 ? pa[e] : T(0), beta, MODE != 0 ? pb[e] : T(0));
-          __stcs(reinterpret_cast<V *>(C + (size_t)j * ldc + i), out);
+          __stcs(reinterpret_cast<V *>(c + i), out);
         }
       }
     } else {
-      if (i >= m) continue;
-      T va[COLS], vb[COLS];
+      T va[UNR], vb[UNR];
 #pragma unroll
-      for (int c = 0; c < COLS; c++) {
-        int j = j0 + c;
-        if (j < n) {
-          if (MODE != 1) va[c] = __ldcs(A + (size_t)j * lda + i);
-          if (MODE != 0) vb[c] = B[(size_t)j * ldb + i];
+      for (int u = 0; u < UNR; u++) {
+        const int i = i0 + u * 256;
+        if (i < m) {
+          if (MODE != 1) va[u] = __ldcs(a + i);
+          if (MODE != 0) vb[u] = b[i];
         }
       }
 #pragma unroll
-      for (int c = 0; c < COLS; c++) {
-        int j = j0 + c;
-        if (j < n) __stcs(C + (size_t)j * ldc + i, axpby<T, MODE>(alpha, MODE != 1 ? va[c] : T(0), beta, MODE != 0 ? vb[c] : T(0)));
+      for (int u = 0; u < UNR; u++) {
+        const int i = i0 + u * 256;
+        if (i < m) __stcs(c + i, axpby<T, MODE>(alpha, MODE != 1 ? va[u] : T(0), beta, MODE != 0 ? vb[u] : T(0)));
       }
     }
   }
@@ -189,16 +256,39 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
     auto aligned = [&](const T *p, int ld) { return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % VN == 0); };
     bool vec = (m % VN == 0) && aligned(C, ldc) && (MODE == 1 || aligned(A, lda)) && (MODE == 0 || aligned(B, ldb));
     if (opt(h, "geam.variant") == 1) vec = false;
-    constexpr int COLS = 4;
-    int rows = 256 * (vec ? VN : 1);
-    int row_tiles = (m + rows - 1) / rows;
-    long long tiles = (long long)row_tiles * ((n + COLS - 1) / COLS);
-    int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+    constexpr int UNR_V = 4, UNR_S = 8;
+    {
+      constexpr int VN32 = Vec32<T>::N;
+      auto aligned32 = [&](const T *p, int ld) { return (reinterpret_cast<uintptr_t>(p) % 32 == 0) && (ld % VN32 == 0); };
+      bool vec32 = (m % VN32 == 0) && aligned32(C, ldc) && (MODE == 1 || aligned32(A, lda)) && (MODE == 0 || aligned32(B, ldb)) &&
+                   opt(h, "geam.variant") == 0;
+      if (vec32) {
+        const int tune = opt(h, "geam.tune");
+        auto go = [&](auto unr_tag, int ctas_per_sm) {
+          constexpr int UNR = decltype(unr_tag)::value;
+          const int chunk32 = 256 * VN32 * UNR;
+          const int cpc = (m + chunk32 - 1) / chunk32;
+          const long long tot = (long long)cpc * n;
+          const long long cap = (long long)h->sm_count * ctas_per_sm;
+          const int g = (int)(tot < cap ? tot : cap);
+          geam_stream256_kernel<T, MODE, UNR><<<g, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, cpc);
+          return check_launch(h, "geam_stream_vec32");
+        };
+        // measured on 8192^2 f64 (GB/s): UNR 4 x 8 CTAs/SM 6333 | 1 x 16: 6252 | 2 x 8: 6082 | 2 x 4: 6051 | 1 x 8: 5975
+        if (tune == 1) return go(std::integral_constant<int, 2>{}, 8);
+        if (tune == 2) return go(std::integral_constant<int, 1>{}, 16);
+        return go(std::integral_constant<int, 4>{}, 8);
+      }
+    }
+    const int chunk = 256 * (vec ? VN * UNR_V : UNR_S);
+    const int chunks_per_col = (m + chunk - 1) / chunk;
+    const long long total = (long long)chunks_per_col * n;
+    const int grid = (int)(total < max_ctas ? total : max_ctas);
     if (vec) {
-      geam_stream_kernel<T, MODE, true, COLS><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, row_tiles);
+      geam_stream_kernel<T, MODE, true, UNR_V><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col);
       return check_launch(h, "geam_stream_vec16");
     }
-    geam_stream_kernel<T, MODE, false, COLS><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, row_tiles);
+    geam_stream_kernel<T, MODE, false, UNR_S><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col);
     return check_launch(h, "geam_stream_scalar");
   }
   const int TL = (ta && tb) ? 32 : 64;

@@ -18,6 +18,10 @@
  *   gpu::blasSgemm         (:98)              rtat_b200_sgemm
  *   gpu::blasDgeam         (:93)              rtat_b200_dgeam
  *   gpu::blasSgeam         (:97)              rtat_b200_sgeam
+ *   gpu::blasDsyrk         (:96)              rtat_b200_dsyrk
+ *   gpu::blasSsyrk         (:100)             rtat_b200_ssyrk
+ *   gpu::blasDtrsm         (:95)              rtat_b200_dtrsm
+ *   gpu::blasStrsm         (:99)              rtat_b200_strsm
  *   gpu::randGenerateUniform[Double] (:119-120)  rtat_b200_fill_uniform_{s,d}   (seeded; drivers only)
  *
  * There is no CPU fallback and no vendor-BLAS call behind these functions: they launch hand-written
@@ -52,6 +56,11 @@ enum {
 
 /* ---- operation flags (cublasOperation_t numbering; reference gpu-api.h:112-113) --------------- */
 enum { RTAT_B200_OP_N = 0, RTAT_B200_OP_T = 1 };
+/* ---- triangle / side / diagonal flags (cublasFillMode_t, cublasSideMode_t, cublasDiagType_t numbering;
+ *      reference gpu-api.h:103-111) ------------------------------------------------------------- */
+enum { RTAT_B200_FILL_LOWER = 0, RTAT_B200_FILL_UPPER = 1 };
+enum { RTAT_B200_SIDE_LEFT = 0, RTAT_B200_SIDE_RIGHT = 1 };
+enum { RTAT_B200_DIAG_NON_UNIT = 0, RTAT_B200_DIAG_UNIT = 1 };
 
 typedef struct rtat_b200_context *rtat_b200_handle_t;
 
@@ -89,6 +98,26 @@ int rtat_b200_dgeam(rtat_b200_handle_t handle, int transa, int transb, int m, in
 int rtat_b200_sgeam(rtat_b200_handle_t handle, int transa, int transb, int m, int n,
                     const float *alpha, const float *A, int lda, const float *beta, const float *B,
                     int ldb, float *C, int ldc);
+
+/* ---- SYRK:  C = alpha * op(A) * op(A)^T + beta * C  on the `uplo` triangle   (replaces cublasDsyrk / cublasSsyrk)
+ * C is n x n; op(A) is n x k (trans == N: A is n x k, lda >= n; trans == T: A is k x n, lda >= k).  Only the
+ * requested triangle of C (diagonal included) is read or written; beta == 0 means it is write-only;
+ * alpha == 0 or k == 0 scales the triangle by beta without reading A.  Runs the GEMM kernels' triangular
+ * tile schedule (syrk.cu), so precision and alignment rules are those of rtat_b200_dgemm / _sgemm. */
+int rtat_b200_dsyrk(rtat_b200_handle_t handle, int uplo, int trans, int n, int k, const double *alpha,
+                    const double *A, int lda, const double *beta, double *C, int ldc);
+int rtat_b200_ssyrk(rtat_b200_handle_t handle, int uplo, int trans, int n, int k, const float *alpha,
+                    const float *A, int lda, const float *beta, float *C, int ldc);
+
+/* ---- TRSM:  op(A) X = alpha B (side LEFT) or X op(A) = alpha B (side RIGHT), X overwrites B   (replaces
+ *      cublasDtrsm / cublasStrsm) ------------------------------------------------------------------
+ * B is m x n; A is triangular (`uplo`), m x m for LEFT, n x n for RIGHT; only that triangle is read, and not its
+ * diagonal when diag == UNIT.  alpha == 0 zeroes B without reading A.  Recursive blocked substitution whose
+ * updates run in the GEMM kernels above (trsm.cu); no inverted diagonal blocks, true divisions. */
+int rtat_b200_dtrsm(rtat_b200_handle_t handle, int side, int uplo, int trans, int diag, int m, int n,
+                    const double *alpha, const double *A, int lda, double *B, int ldb);
+int rtat_b200_strsm(rtat_b200_handle_t handle, int side, int uplo, int trans, int diag, int m, int n,
+                    const float *alpha, const float *A, int lda, float *B, int ldb);
 
 /* ---- seeded uniform fill in (lo, hi]  (replaces the unseeded cuRAND fill of the drivers) -------
  * Counter-based (SplitMix64 of seed + element index): the same (seed, index) gives the same value

@@ -40,6 +40,20 @@ int rtat_host_planner_gemm(rtat_host_planner_t planner, rtat_b200_handle_t handl
 /* bytes of workspace `plan` needs for this problem */
 long long rtat_host_planner_workspace(rtat_host_planner_t planner, int transa, int transb, int m, int n, int k, int lda, int ldb,
                                       int ldc, const char *plan);
+/* SYRK / TRSM through their planners (reference src/rtat.h:23-26 syrk_planner / trsm_planner; plan strings are the
+ * two Bool_Op letters of SYRK_Options "ac" / TRSM_Options "sa", e.g. "FT").  The planner must have been created with
+ * method "syrk" / "trsm"; other planners fail with -1.  Arguments as in rtat_b200_{d,s}syrk / _trsm; alpha/beta point
+ * to host scalars of the planner's data type. */
+int rtat_host_planner_syrk(rtat_host_planner_t planner, rtat_b200_handle_t handle, int uplo, int trans, int n, int k, const void *alpha,
+                           const void *A, int lda, const void *beta, void *C, int ldc, void *workspace, size_t workspace_bytes,
+                           const char *forced_plan, char *plan_out);
+long long rtat_host_planner_syrk_workspace(rtat_host_planner_t planner, int uplo, int trans, int n, int k, int lda, int ldc,
+                                           const char *plan);
+int rtat_host_planner_trsm(rtat_host_planner_t planner, rtat_b200_handle_t handle, int side, int uplo, int trans, int diag, int m, int n,
+                           const void *alpha, const void *A, int lda, void *B, int ldb, void *workspace, size_t workspace_bytes,
+                           const char *forced_plan, char *plan_out);
+long long rtat_host_planner_trsm_workspace(rtat_host_planner_t planner, int side, int uplo, int trans, int diag, int m, int n, int lda,
+                                           int ldb, const char *plan);
 char *rtat_host_planner_statistics(rtat_host_planner_t planner);
 char *rtat_host_planner_save_plans(rtat_host_planner_t planner);
 long long rtat_host_planner_load_plans(rtat_host_planner_t planner, const char *json_text);

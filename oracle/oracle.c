@@ -44,6 +44,32 @@ size_t oracle_gemm_plan_workspace(const char *plan, int transa, int transb, int 
   return ws * elem_size;
 }
 
+static int parse_bool_plan(const char *plan) {
+  if (!plan || strlen(plan) != 2) return 1;
+  for (int i = 0; i < 2; i++)
+    if (plan[i] != 'F' && plan[i] != 'T') return 1;
+  return 0;
+}
+
+/* workspace_req of the SYRK trees (syrk.cpp:72-104): [transpose_C] n*n + [transpose_A] footprint(A^T) */
+size_t oracle_syrk_plan_workspace(const char *plan, int trans, int n, int k, size_t elem_size) {
+  (void)trans;
+  if (parse_bool_plan(plan)) return (size_t)-1;
+  size_t ws = 0;
+  if (plan[0] == 'T') ws += (size_t)n * k;
+  if (plan[1] == 'T') ws += (size_t)n * n;
+  return ws * elem_size;
+}
+
+/* workspace_req of the TRSM trees (trsm.cpp:72-113): [swap_side] n*m (B^T) + [transpose_A] na*na */
+size_t oracle_trsm_plan_workspace(const char *plan, int left, int m, int n, size_t elem_size) {
+  if (parse_bool_plan(plan)) return (size_t)-1;
+  size_t na = left ? m : n, ws = 0;
+  if (plan[1] == 'T') ws += na * na;
+  if (plan[0] == 'T') ws += (size_t)n * m;
+  return ws * elem_size;
+}
+
 #define T double
 #define SUF d
 #define WIDE long double

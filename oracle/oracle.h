@@ -64,6 +64,32 @@ int oracle_sgemm_plan(const char *plan, int transa, int transb, int m, int n, in
                       const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc,
                       void *workspace, size_t workspace_bytes);
 
+/* SYRK / TRSM.  The reference holds no CPU restatement of either: its tests check
+ * SYRK against its own GEMM and TRSM by solving a product back (tests/executor_test.cpp:132-290).  These follow
+ * the BLAS definitions the reference's cuBLAS calls implement (matrixop.h:48-109), with test_gemm's element
+ * arithmetic; lower/trans/left/unit are 0/1 flags. */
+void oracle_dsyrk(int lower, int trans, int n, int k, double alpha, const double *A, int lda, double beta,
+                  double *C, int ldc);
+void oracle_ssyrk(int lower, int trans, int n, int k, float alpha, const float *A, int lda, float beta, float *C,
+                  int ldc);
+void oracle_dtrsm(int left, int lower, int trans, int unit, int m, int n, double alpha, const double *A, int lda,
+                  double *B, int ldb);
+void oracle_strsm(int left, int lower, int trans, int unit, int m, int n, float alpha, const float *A, int lda,
+                  float *B, int ldb);
+/* Plan algebra: SYRK_Options "ac" (transpose_A, transpose_C; src/methods/syrk.cpp:72-104) and TRSM_Options "sa"
+ * (swap_side, transpose_A; src/methods/trsm.cpp:72-113), letters F/T.  Same return conventions as the GEMM
+ * plan functions above. */
+size_t oracle_syrk_plan_workspace(const char *plan, int trans, int n, int k, size_t elem_size);
+size_t oracle_trsm_plan_workspace(const char *plan, int left, int m, int n, size_t elem_size);
+int oracle_dsyrk_plan(const char *plan, int lower, int trans, int n, int k, double alpha, const double *A, int lda,
+                      double beta, double *C, int ldc, void *workspace, size_t workspace_bytes);
+int oracle_ssyrk_plan(const char *plan, int lower, int trans, int n, int k, float alpha, const float *A, int lda,
+                      float beta, float *C, int ldc, void *workspace, size_t workspace_bytes);
+int oracle_dtrsm_plan(const char *plan, int left, int lower, int trans, int unit, int m, int n, double alpha,
+                      const double *A, int lda, double *B, int ldb, void *workspace, size_t workspace_bytes);
+int oracle_strsm_plan(const char *plan, int left, int lower, int trans, int unit, int m, int n, float alpha,
+                      const float *A, int lda, float *B, int ldb, void *workspace, size_t workspace_bytes);
+
 /* Same counter-based generator as rtat_b200_fill_uniform_{d,s} (seeded replacement of the
  * reference drivers' unseeded cuRAND fill, src/app/test_harness.h:176). */
 void oracle_fill_uniform_d(double *x, size_t n, uint64_t seed, double lo, double hi);

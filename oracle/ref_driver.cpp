@@ -4,6 +4,7 @@
 // Built by oracle/Makefile into oracle/_ref/ (git-ignored).  TEST INFRASTRUCTURE ONLY.
 //
 //   ref_driver golden <out.bin> <out.json>      run the fixed golden case list (needs a GPU)
+//   ref_driver golden_l3 <out.bin> <out.json>   SYRK / TRSM executors and raw calls (needs a GPU)
 //
 // Inputs use the same counter-based generator as oracle_fill_uniform_* / rtat_b200_fill_uniform_*
 // so the consumers regenerate them from (seed, count) instead of storing them.
@@ -14,6 +15,8 @@
 #include <vector>
 #include <gemm.h>       // reference: src/methods/gemm.h
 #include <matrixop.h>   // reference: src/matrix_ops/matrixop.h
+#include <syrk.h>       // reference: src/methods/syrk.h
+#include <trsm.h>       // reference: src/methods/trsm.h
 
 using namespace rtat;
 
@@ -216,11 +219,127 @@ static void all_cases(Sink &out, gpu::blasHandle_t handle, Stream s, uint64_t ba
     }
 }
 
+// SYRK_Executor over all four plans (executor_test.cpp:227-290 walks the same loops); the WHOLE of C is dumped so
+// that what each plan does to the triangle BLAS leaves alone is pinned too.
+template <typename T>
+static void syrk_plan_case(Sink &out, gpu::blasHandle_t handle, Stream s, bool lower, bool trans, int n, int k, T alpha,
+                           T beta, uint64_t seed) {
+  for (auto &opts : SYRK_Options::enumerate()) {
+    size_t ar = trans ? k : n, ac = trans ? n : k;
+    DevMat<T> A(ar, ac, ar, seed), C(n, n, n, seed + 1);
+    SYRK_Inputs<T> in(handle, lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER,
+                      trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, A.matrix(), C.matrix(), alpha, beta);
+    SYRK_Executor<T> exec;
+    size_t ws = exec.calculate_workspace(in, opts);
+    ManagedWorkspace space(ws + 16);
+    gpuAssert(gpu::Memset(space, 0xFF, ws + 16));  // NaN-patterned scratch: shows whether geam(0, 0) really clears it
+    Workspace exact((char *)space, ws);
+    exec.execute(in, opts, exact, s);
+    s.synchronize();
+    C.download();
+    std::string meta = kvs("kind", "syrk_plan") + ", " + kvs("plan", std::string(opts)) + ", " + kv("lower", lower) + ", " +
+                       kv("trans", trans) + ", " + kv("n", n) + ", " + kv("k", k) + ", " + kvd("alpha", alpha) + ", " +
+                       kvd("beta", beta) + ", " + kv("seed", seed) + ", " + kv("workspace_bytes", (long long)ws) + ", " +
+                       kvs("key", std::string(SYRK_Key(in)));
+    out.emit(meta, C.host);
+  }
+}
+
+template <typename T>
+static void raw_syrk_case(Sink &out, gpu::blasHandle_t handle, Stream s, bool lower, bool trans, int n, int k, T alpha,
+                          T beta, uint64_t seed) {
+  size_t ar = trans ? k : n, ac = trans ? n : k;
+  DevMat<T> A(ar, ac, ar + 3, seed), C(n, n, n + 2, seed + 1);
+  gpuTsyrk<T>(handle, lower, trans, A.matrix(), C.matrix(), alpha, beta);
+  s.synchronize();
+  C.download();
+  std::string meta = kvs("kind", "raw_syrk") + ", " + kv("lower", lower) + ", " + kv("trans", trans) + ", " + kv("n", n) +
+                     ", " + kv("k", k) + ", " + kv("lda", ar + 3) + ", " + kv("ldc", n + 2) + ", " + kvd("alpha", alpha) +
+                     ", " + kvd("beta", beta) + ", " + kv("seed", seed);
+  out.emit(meta, C.host);
+}
+
+// Triangular test matrix: uniform fill, then the diagonal is pushed away from zero (non-unit) or the
+// off-diagonals are shrunk (unit), as executor_test.cpp:146-176 does; the unused triangle keeps its random
+// contents so that reading it would show.
+template <typename T>
+static void condition_triangle(DevMat<T> &A, bool unit) {
+  size_t n = A.m;
+  for (size_t j = 0; j < n; j++)
+    for (size_t i = 0; i < n; i++) {
+      T &a = A.host[j * A.ld + i];
+      if (i == j && !unit) a += (a < 0 ? -(T)2 : (T)2);
+      if (i != j) a /= (T)4;
+    }
+  A.upload();
+}
+
+template <typename T>
+static void trsm_plan_case(Sink &out, gpu::blasHandle_t handle, Stream s, bool left, bool lower, bool trans, bool unit,
+                           int m, int n, T alpha, uint64_t seed) {
+  for (auto &opts : TRSM_Options::enumerate()) {
+    size_t na = left ? m : n;
+    DevMat<T> A(na, na, na, seed), B(m, n, m, seed + 1);
+    condition_triangle(A, unit);
+    TRSM_Inputs<T> in(handle, left ? gpu::BLAS_SIDE_LEFT : gpu::BLAS_SIDE_RIGHT,
+                      lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N,
+                      unit ? gpu::BLAS_DIAG_UNIT : gpu::BLAS_DIAG_NON_UNIT, A.matrix(), B.matrix(), alpha);
+    TRSM_Executor<T> exec;
+    size_t ws = exec.calculate_workspace(in, opts);
+    ManagedWorkspace space(ws + 16);
+    gpuAssert(gpu::Memset(space, 0xFF, ws + 16));
+    Workspace exact((char *)space, ws);
+    exec.execute(in, opts, exact, s);
+    s.synchronize();
+    B.download();
+    std::string meta = kvs("kind", "trsm_plan") + ", " + kvs("plan", std::string(opts)) + ", " + kv("left", left) + ", " +
+                       kv("lower", lower) + ", " + kv("trans", trans) + ", " + kv("unit", unit) + ", " + kv("m", m) + ", " +
+                       kv("n", n) + ", " + kvd("alpha", alpha) + ", " + kv("seed", seed) + ", " +
+                       kv("workspace_bytes", (long long)ws) + ", " + kvs("key", std::string(TRSM_Key(in)));
+    out.emit(meta, B.host);
+  }
+}
+
+template <typename T>
+static void raw_trsm_case(Sink &out, gpu::blasHandle_t handle, Stream s, bool left, bool lower, bool trans, bool unit, int m,
+                          int n, T alpha, uint64_t seed) {
+  size_t na = left ? m : n;
+  DevMat<T> A(na, na, na + 1, seed), B(m, n, m + 3, seed + 1);
+  condition_triangle(A, unit);
+  gpuTtrsm<T>(handle, left, lower, trans, unit, A.matrix(), B.matrix(), alpha);
+  s.synchronize();
+  B.download();
+  std::string meta = kvs("kind", "raw_trsm") + ", " + kv("left", left) + ", " + kv("lower", lower) + ", " + kv("trans", trans) +
+                     ", " + kv("unit", unit) + ", " + kv("m", m) + ", " + kv("n", n) + ", " + kv("lda", na + 1) + ", " +
+                     kv("ldb", m + 3) + ", " + kvd("alpha", alpha) + ", " + kv("seed", seed);
+  out.emit(meta, B.host);
+}
+
+template <typename T>
+static void l3_cases(Sink &out, gpu::blasHandle_t handle, Stream s, uint64_t base) {
+  uint64_t seed = base;
+  for (bool lower : {false, true})
+    for (bool trans : {false, true}) {
+      syrk_plan_case<T>(out, handle, s, lower, trans, 37, 19, (T)1, (T)0, seed); seed += 2;     // harness defaults (test_harness.h:274-277)
+      syrk_plan_case<T>(out, handle, s, lower, trans, 21, 30, (T)-1, (T)1, seed); seed += 2;    // executor_test.cpp:262-266
+      raw_syrk_case<T>(out, handle, s, lower, trans, 45, 23, (T)0.75, (T)-0.5, seed); seed += 2;
+      raw_syrk_case<T>(out, handle, s, lower, trans, 18, 9, (T)0, (T)2, seed); seed += 2;       // alpha == 0: scale only
+    }
+  for (bool left : {false, true})
+    for (bool lower : {false, true})
+      for (bool trans : {false, true})
+        for (bool unit : {false, true}) {
+          trsm_plan_case<T>(out, handle, s, left, lower, trans, unit, 21, 17, (T)1, seed); seed += 2;
+          raw_trsm_case<T>(out, handle, s, left, lower, trans, unit, 40, 33, (T)-1.5, seed); seed += 2;
+        }
+}
+
 int main(int argc, char **argv) {
-  if (argc != 4 || std::string(argv[1]) != "golden") {
-    fprintf(stderr, "usage: ref_driver golden <out.bin> <out.json>\n");
+  if (argc != 4 || (std::string(argv[1]) != "golden" && std::string(argv[1]) != "golden_l3")) {
+    fprintf(stderr, "usage: ref_driver golden|golden_l3 <out.bin> <out.json>\n");
     return 2;
   }
+  const bool l3 = std::string(argv[1]) == "golden_l3";
   Sink out;
   out.bin = fopen(argv[2], "wb");
   out.json = fopen(argv[3], "w");
@@ -230,8 +349,13 @@ int main(int argc, char **argv) {
   gpu::blasCreate(&handle);
   gpu::blasSetStream(handle, s);
   fprintf(out.json, "{\"generator\": \"oracle/ref_driver.cpp golden (reference executor + cuBLAS)\", \"cases\": [");
-  all_cases<double>(out, handle, s, 1000);
-  all_cases<float>(out, handle, s, 5000);
+  if (l3) {
+    l3_cases<double>(out, handle, s, 20000);
+    l3_cases<float>(out, handle, s, 30000);
+  } else {
+    all_cases<double>(out, handle, s, 1000);
+    all_cases<float>(out, handle, s, 5000);
+  }
   fprintf(out.json, "\n]}\n");
   fclose(out.bin);
   fclose(out.json);

@@ -59,6 +59,8 @@ def _declare(L):
         getattr(L, f"rtat_b200_{name}gemm").argtypes = [vp, i, i, i, i, i, sp, vp, i, vp, i, sp, vp, i]
         getattr(L, f"rtat_b200_{name}gemm_host").argtypes = [vp, i, i, i, i, i, sp, vp, i, vp, i, sp, vp, i]
         getattr(L, f"rtat_b200_{name}geam").argtypes = [vp, i, i, i, i, sp, vp, i, sp, vp, i, vp, i]
+        getattr(L, f"rtat_b200_{name}syrk").argtypes = [vp, i, i, i, i, sp, vp, i, sp, vp, i]
+        getattr(L, f"rtat_b200_{name}trsm").argtypes = [vp, i, i, i, i, i, i, sp, vp, i, vp, i]
     L.rtat_b200_fill_uniform_d.argtypes = [vp, vp, sz, u64, C.c_double, C.c_double]
     L.rtat_b200_fill_uniform_s.argtypes = [vp, vp, sz, u64, C.c_float, C.c_float]
     L.rtat_b200_set_option.argtypes = [vp, C.c_char_p, i]
@@ -146,6 +148,22 @@ class Handle:
         fn = getattr(lib(), f"rtat_b200_{'d' if double else 's'}geam")
         st = fn(self._h, transa, transb, m, n, self._scal(double, alpha), _ptr(A), lda,
                 self._scal(double, beta), _ptr(B), ldb, _ptr(Cm), ldc)
+        if check:
+            _check(st, fn.__name__)
+        return st
+
+    def syrk(self, double, uplo, trans, n, k, alpha, A, lda, beta, Cm, ldc, check=True):
+        """uplo: 0 lower / 1 upper (RTAT_B200_FILL_*); trans: 0 N / 1 T."""
+        fn = getattr(lib(), f"rtat_b200_{'d' if double else 's'}syrk")
+        st = fn(self._h, uplo, trans, n, k, self._scal(double, alpha), _ptr(A), lda, self._scal(double, beta), _ptr(Cm), ldc)
+        if check:
+            _check(st, fn.__name__)
+        return st
+
+    def trsm(self, double, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, check=True):
+        """side: 0 left / 1 right; uplo: 0 lower / 1 upper; trans: 0 N / 1 T; diag: 0 non-unit / 1 unit."""
+        fn = getattr(lib(), f"rtat_b200_{'d' if double else 's'}trsm")
+        st = fn(self._h, side, uplo, trans, diag, m, n, self._scal(double, alpha), _ptr(A), lda, _ptr(B), ldb)
         if check:
             _check(st, fn.__name__)
         return st

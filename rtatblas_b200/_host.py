@@ -27,6 +27,12 @@ def host_lib():
         L.rtat_host_planner_gemm.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, vp, i, vp, sz, cp, cp]
         L.rtat_host_planner_workspace.restype = ll
         L.rtat_host_planner_workspace.argtypes = [vp, i, i, i, i, i, i, i, i, cp]
+        L.rtat_host_planner_syrk.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, vp, i, vp, sz, cp, cp]
+        L.rtat_host_planner_syrk_workspace.restype = ll
+        L.rtat_host_planner_syrk_workspace.argtypes = [vp, i, i, i, i, i, i, cp]
+        L.rtat_host_planner_trsm.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, i, vp, i, vp, sz, cp, cp]
+        L.rtat_host_planner_trsm_workspace.restype = ll
+        L.rtat_host_planner_trsm_workspace.argtypes = [vp, i, i, i, i, i, i, i, i, cp]
         for n in ("statistics", "save_plans"):
             getattr(L, f"rtat_host_planner_{n}").restype = vp
             getattr(L, f"rtat_host_planner_{n}").argtypes = [vp]
@@ -94,6 +100,40 @@ class Planner:
                                                plan.encode() if plan else None, out)
         if rc != 0:
             raise RtatError("planner gemm failed: " + host_lib().rtat_host_last_error().decode())
+        return out.value.decode()
+
+    def syrk_workspace(self, uplo, trans, n, k, plan, lda=None, ldc=None):
+        r = host_lib().rtat_host_planner_syrk_workspace(self._p, uplo, trans, n, k, lda or (k if trans else n), ldc or n, plan.encode())
+        if r < 0:
+            raise RtatError(host_lib().rtat_host_last_error().decode())
+        return r
+
+    def syrk(self, handle: Handle, uplo, trans, n, k, alpha, A, lda, beta, Cm, ldc, workspace=None, workspace_bytes=0, plan=None):
+        """SYRK through Planning_System<SYRK_Executor>; returns the plan used ("FF", "FT", "TF" or "TT")."""
+        ct = C.c_double if self.double else C.c_float
+        al, be = ct(alpha), ct(beta)
+        out = C.create_string_buffer(16)
+        rc = host_lib().rtat_host_planner_syrk(self._p, handle.raw, uplo, trans, n, k, C.byref(al), _ptr(A), lda, C.byref(be), _ptr(Cm), ldc,
+                                               _ptr(workspace), workspace_bytes, plan.encode() if plan else None, out)
+        if rc != 0:
+            raise RtatError("planner syrk failed: " + host_lib().rtat_host_last_error().decode())
+        return out.value.decode()
+
+    def trsm_workspace(self, side, uplo, trans, diag, m, n, plan, lda=None, ldb=None):
+        r = host_lib().rtat_host_planner_trsm_workspace(self._p, side, uplo, trans, diag, m, n, lda or (n if side else m), ldb or m,
+                                                        plan.encode())
+        if r < 0:
+            raise RtatError(host_lib().rtat_host_last_error().decode())
+        return r
+
+    def trsm(self, handle: Handle, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, workspace=None, workspace_bytes=0, plan=None):
+        """TRSM through Planning_System<TRSM_Executor>; returns the plan used."""
+        al = (C.c_double if self.double else C.c_float)(alpha)
+        out = C.create_string_buffer(16)
+        rc = host_lib().rtat_host_planner_trsm(self._p, handle.raw, side, uplo, trans, diag, m, n, C.byref(al), _ptr(A), lda, _ptr(B), ldb,
+                                               _ptr(workspace), workspace_bytes, plan.encode() if plan else None, out)
+        if rc != 0:
+            raise RtatError("planner trsm failed: " + host_lib().rtat_host_last_error().decode())
         return out.value.decode()
 
     def statistics(self):

@@ -166,6 +166,70 @@ int rtat_b200_sgemm(rtat_b200_handle_t h, int transa, int transb, int m, int n, 
   return sgemm(h, transa, transb, m, n, k, *alpha, A, lda, B, ldb, *beta, C, ldc);
 }
 
+static int validate_syrk(int uplo, int trans, int n, int k, int lda, int ldc) {
+  if (uplo != RTAT_B200_FILL_LOWER && uplo != RTAT_B200_FILL_UPPER) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (trans != RTAT_B200_OP_N && trans != RTAT_B200_OP_T) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (n < 0 || k < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  int rows_a = trans == RTAT_B200_OP_N ? n : k;
+  if (lda < (rows_a > 1 ? rows_a : 1) || ldc < (n > 1 ? n : 1)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_dsyrk(rtat_b200_handle_t h, int uplo, int trans, int n, int k, const double *alpha, const double *A,
+                    int lda, const double *beta, double *C, int ldc) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_syrk(uplo, trans, n, k, lda, ldc);
+  if (st) return st;
+  if (n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!C || (k > 0 && *alpha != 0.0 && !A)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return dsyrk(h, uplo, trans, n, k, *alpha, A, lda, *beta, C, ldc);
+}
+
+int rtat_b200_ssyrk(rtat_b200_handle_t h, int uplo, int trans, int n, int k, const float *alpha, const float *A,
+                    int lda, const float *beta, float *C, int ldc) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_syrk(uplo, trans, n, k, lda, ldc);
+  if (st) return st;
+  if (n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!C || (k > 0 && *alpha != 0.f && !A)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return ssyrk(h, uplo, trans, n, k, *alpha, A, lda, *beta, C, ldc);
+}
+
+static int validate_trsm(int side, int uplo, int trans, int diag, int m, int n, int lda, int ldb) {
+  if (side != RTAT_B200_SIDE_LEFT && side != RTAT_B200_SIDE_RIGHT) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (uplo != RTAT_B200_FILL_LOWER && uplo != RTAT_B200_FILL_UPPER) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (trans != RTAT_B200_OP_N && trans != RTAT_B200_OP_T) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (diag != RTAT_B200_DIAG_NON_UNIT && diag != RTAT_B200_DIAG_UNIT) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (m < 0 || n < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  int na = side == RTAT_B200_SIDE_LEFT ? m : n;
+  if (lda < (na > 1 ? na : 1) || ldb < (m > 1 ? m : 1)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_dtrsm(rtat_b200_handle_t h, int side, int uplo, int trans, int diag, int m, int n, const double *alpha,
+                    const double *A, int lda, double *B, int ldb) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_trsm(side, uplo, trans, diag, m, n, lda, ldb);
+  if (st) return st;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!B || (*alpha != 0.0 && !A)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return dtrsm(h, side, uplo, trans, diag, m, n, *alpha, A, lda, B, ldb);
+}
+
+int rtat_b200_strsm(rtat_b200_handle_t h, int side, int uplo, int trans, int diag, int m, int n, const float *alpha,
+                    const float *A, int lda, float *B, int ldb) {
+  if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!alpha) return RTAT_B200_STATUS_INVALID_VALUE;
+  int st = validate_trsm(side, uplo, trans, diag, m, n, lda, ldb);
+  if (st) return st;
+  if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
+  if (!B || (*alpha != 0.f && !A)) return RTAT_B200_STATUS_INVALID_VALUE;
+  return strsm(h, side, uplo, trans, diag, m, n, *alpha, A, lda, B, ldb);
+}
+
 }  // extern "C"
 
 template <typename T>

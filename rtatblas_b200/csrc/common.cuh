@@ -69,6 +69,16 @@ int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, dou
 int sgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
           const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
 
+int dsyrk(rtat_b200_context *h, int uplo, int trans, int n, int k, double alpha, const double *A, int lda, double beta,
+          double *C, int ldc);
+int ssyrk(rtat_b200_context *h, int uplo, int trans, int n, int k, float alpha, const float *A, int lda, float beta,
+          float *C, int ldc);
+
+int dtrsm(rtat_b200_context *h, int side, int uplo, int trans, int diag, int m, int n, double alpha, const double *A, int lda, double *B,
+          int ldb);
+int strsm(rtat_b200_context *h, int side, int uplo, int trans, int diag, int m, int n, float alpha, const float *A, int lda, float *B,
+          int ldb);
+
 template <typename T>
 int fill_uniform(rtat_b200_context *h, T *x, size_t n, uint64_t seed, T lo, T hi);
 

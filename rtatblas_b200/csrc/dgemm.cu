@@ -219,7 +219,7 @@ static int launch_ops(rtat_b200_context *h, DgemmParams &p, int variant) {
 }
 
 int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
-             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg);
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg, int tri = 0);
 
 int dgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, double alpha,
           const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc) {

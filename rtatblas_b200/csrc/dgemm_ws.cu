@@ -68,7 +68,18 @@ struct Params {
   double *sk_slots;        // gridDim.x slots of CONSUMER_WARPS*32*64 doubles
   unsigned *sk_flags;      // gridDim.x flags, compared against sk_generation
   unsigned sk_generation;
+  // SYRK (TRI kernels): 1 = only the lower triangle of C is computed and written, 2 = upper.  Tiles are
+  // then the tiles_m (tiles_m + 1) / 2 tiles that touch the triangle, numbered row by row.
+  int tri;
 };
+
+// Tile t of a triangular enumeration -> (i, j) with i >= j: t = i (i + 1) / 2 + j.
+__device__ __forceinline__ void tri_decode(int t, int &i, int &j) {
+  i = int((__fsqrt_rn(8.0f * float(t) + 1.0f) - 1.0f) * 0.5f);
+  while ((long long)i * (i + 1) / 2 > t) i--;
+  while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
+  j = t - int((long long)i * (i + 1) / 2);
+}
 
 // One contiguous piece of work: k-tiles [kb, ke) of `tile`.
 struct Segment {
@@ -234,7 +245,7 @@ __device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *
   }
 }
 
-template <class Cfg, bool TA, bool TB, bool USE_TMA>
+template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
 __global__ void __launch_bounds__((Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, Cfg::CTAS_PER_SM)
 dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
@@ -258,6 +269,13 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
 
   auto tile_coords = [&](int tile, int &m0, int &n0) {
+    if (TRI) {
+      int i, j;
+      tri_decode(tile, i, j);
+      m0 = (p.tri == 1 ? i : j) * BM;
+      n0 = (p.tri == 1 ? j : i) * BN;
+      return;
+    }
     constexpr int GROUP = 8;
     int group_size = GROUP * p.tiles_n;
     int first_m = (tile / group_size) * GROUP;
@@ -423,6 +441,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < MI; i++) {
           int row = m0 + wm0 + phys_index<KCA>(i, g);
+          if (TRI && (p.tri == 1 ? row < col : row > col)) continue;
           if (row < p.m) {
             double v = alpha * acc[i][j][e];
             if (beta != 0.0) v += beta * ccol[row];
@@ -454,9 +473,9 @@ static bool make_map(CUtensorMap *map, const double *base, uint64_t dim0, uint64
   return r == CUDA_SUCCESS;
 }
 
-template <class Cfg, bool TA, bool TB, bool USE_TMA>
+template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
 static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap &ma, const CUtensorMap &mb, const char *name) {
-  auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA>;
+  auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
   constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
   static bool configured = false;
@@ -481,11 +500,11 @@ bool dgemm_ws_tma_ok(const double *A, int lda, const double *B, int ldb) {
 
 // Stream-K finishers spin on flags raised by other CTAs, so every CTA of the grid must be resident at
 // once: never launch more CTAs than the occupancy calculator says fit.
-template <class Cfg, bool TA, bool TB, bool USE_TMA>
+template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
 static int resident_ctas_per_sm() {
   static int cached = -1;
   if (cached < 0) {
-    auto kern = ws::dgemm_ws_kernel<Cfg, TA, TB, USE_TMA>;
+    auto kern = ws::dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     int occ = 0;
     int threads = (Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : ws::CPASYNC_PRODUCER_WARPS)) * 32;
@@ -498,7 +517,11 @@ static int resident_ctas_per_sm() {
   return cached;
 }
 template <class Cfg>
-static int resident_ctas_per_sm(bool ta, bool tb, bool tma) {
+static int resident_ctas_per_sm(bool ta, bool tb, bool tma, bool tri) {
+  if (tri) {
+    if (ta) return tma ? resident_ctas_per_sm<Cfg, true, false, true, true>() : resident_ctas_per_sm<Cfg, true, false, false, true>();
+    return tma ? resident_ctas_per_sm<Cfg, false, true, true, true>() : resident_ctas_per_sm<Cfg, false, true, false, true>();
+  }
 #define RTAT_OCC(TA_, TB_) (tma ? resident_ctas_per_sm<Cfg, TA_, TB_, true>() : resident_ctas_per_sm<Cfg, TA_, TB_, false>())
   if (!ta && !tb) return RTAT_OCC(false, false);
   if (ta && !tb) return RTAT_OCC(true, false);
@@ -509,7 +532,7 @@ static int resident_ctas_per_sm(bool ta, bool tb, bool tma) {
 
 template <class Cfg>
 static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B,
-                   int ldb, double beta, double *C, int ldc, bool allow_tma, const char *tile_name) {
+                   int ldb, double beta, double *C, int ldc, bool allow_tma, const char *tile_name, int tri) {
   using namespace ws;
   constexpr int BM = Cfg::BM, BN = Cfg::BN;
   Params p{};
@@ -519,6 +542,11 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   p.tiles_m = (m + BM - 1) / BM;
   p.tiles_n = (n + BN - 1) / BN;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
+  p.tri = tri;
+  if (tri) {
+    if (m != n || ta == tb) return RTAT_B200_STATUS_INVALID_VALUE;
+    tiles = (long long)p.tiles_m * (p.tiles_m + 1) / 2;
+  }
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   p.num_tiles = (int)tiles;
   p.kt = (k + BK - 1) / BK;
@@ -527,7 +555,7 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   constexpr int MIN_UNITS = 4;
   long long units = tiles * p.kt;
   bool use_tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
-  const int max_grid = h->sm_count * resident_ctas_per_sm<Cfg>(ta, tb, use_tma);
+  const int max_grid = h->sm_count * resident_ctas_per_sm<Cfg>(ta, tb, use_tma, tri != 0);
   int grid = max_grid;
   if (units < (long long)grid * MIN_UNITS) grid = (int)((units + MIN_UNITS - 1) / MIN_UNITS);
   if (grid < 1) grid = 1;
@@ -570,7 +598,12 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   }
   // kernel name reported through rtat_b200_last_kernel: dgemm_ws_dmma_<tile>_{tma|cpasync8}[_streamk]
   static thread_local char name[96];
-  snprintf(name, sizeof name, "dgemm_ws_dmma_%s_%s%s", tile_name, use_tma ? "tma" : "cpasync8", sk_tiles ? "_streamk" : "");
+  snprintf(name, sizeof name, "%s_ws_dmma_%s_%s%s", tri ? "dsyrk" : "dgemm", tile_name, use_tma ? "tma" : "cpasync8", sk_tiles ? "_streamk" : "");
+  if (tri) {
+    if (ta)
+      return use_tma ? launch<Cfg, true, false, true, true>(h, p, grid, ma, mb, name) : launch<Cfg, true, false, false, true>(h, p, grid, ma, mb, name);
+    return use_tma ? launch<Cfg, false, true, true, true>(h, p, grid, ma, mb, name) : launch<Cfg, false, true, false, true>(h, p, grid, ma, mb, name);
+  }
 #define RTAT_WS(TA_, TB_) \
   (use_tma ? launch<Cfg, TA_, TB_, true>(h, p, grid, ma, mb, name) : launch<Cfg, TA_, TB_, false>(h, p, grid, ma, mb, name))
   if (!ta && !tb) return RTAT_WS(false, false);
@@ -580,24 +613,28 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
 #undef RTAT_WS
 }
 
-// tile_cfg: 0 = choose, 128 / 64 = forced
+// tile_cfg: 0 = choose, 128 / 64 = forced.  tri: 0 = GEMM; 1 / 2 = SYRK on the lower / upper triangle (m == n, B is A
+// with the opposite op; only tiles touching the triangle are scheduled and the diagonal tiles are masked).
 int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
-             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg) {
+             const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg, int tri) {
   if (tile_cfg == 0) {
     // Estimated cost = padded tile area x waves.  128x128 tiles are the more efficient steady state
     // (98 % vs ~94 % of the DMMA pipe), 64x64 tiles waste less on ragged edges and keep stream-K fix-ups
     // four times smaller, which decides small problems.
-    auto padded = [&](int bm) { return (double)((m + bm - 1) / bm) * bm * (double)((n + bm - 1) / bm) * bm; };
+    auto padded = [&](int bm) {
+      double tm = (m + bm - 1) / bm, tn = (n + bm - 1) / bm;
+      return (tri ? tm * (tm + 1) / 2 : tm * tn) * bm * bm;
+    };
     // measured steady-state efficiencies: TMA producers 0.98 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
     const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
     double t128 = padded(128) / (tma ? 0.98 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
-    long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16);
+    long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16) / (tri ? 2 : 1);
     bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
     tile_cfg = (small || t64 < t128) ? 64 : 128;
   }
   if (tile_cfg == 64)
-    return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16");
-  return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16");
+    return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);
+  return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
 }
 
 }  // namespace rtat_b200

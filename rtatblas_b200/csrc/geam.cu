@@ -314,6 +314,12 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
 template <typename T>
 int geam(rtat_b200_context *h, int transa, int transb, int m, int n, T alpha, const T *A, int lda,
          T beta, const T *B, int ldb, T *C, int ldc) {
+  if (alpha == T(0) && beta == T(0)) {
+    // neither operand is referenced: C = 0 (MatrixSyrkAlloc clears its scratch this way, reference matrixop.h:612)
+    if (cudaMemset2DAsync(C, sizeof(T) * ldc, 0, sizeof(T) * m, n, h->stream) != cudaSuccess) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    h->last_kernel = "memset2d";
+    return RTAT_B200_STATUS_SUCCESS;
+  }
   if (beta == T(0)) return launch_geam<T, 0>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
   if (alpha == T(0)) return launch_geam<T, 1>(h, transa, transb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
   switch (opt(h, "geam.rounding", 4)) {  // 4 = cuBLAS behaviour; 2/3 kept for experiments

@@ -5,15 +5,24 @@
 namespace rtat_b200 {
 
 int sgemm_simt(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
-               const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+               const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri);
 int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
-                  const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+                  const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri);
 bool sgemm_tcgen05_supported(const rtat_b200_context *h, int transa, int transb, int m, int n, int k,
                              const float *A, int lda, const float *B, int ldb, const float *C, int ldc);
 
+// tri: 0 = GEMM; 1 / 2 = SYRK on the lower / upper triangle (syrk.cu; alpha == 0 and k == 0 are handled there)
+int sgemm_tri(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
+              const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri);
+
 int sgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
           const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc) {
-  if (k == 0 || alpha == 0.f) {
+  return sgemm_tri(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+}
+
+int sgemm_tri(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
+              const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri) {
+  if (!tri && (k == 0 || alpha == 0.f)) {
     if (beta == 0.f) {
       if (cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * m, n, h->stream) != cudaSuccess)
         return RTAT_B200_STATUS_EXECUTION_FAILED;
@@ -30,10 +39,10 @@ int sgemm(rtat_b200_context *h, int transa, int transb, int m, int n, int k, flo
   // small that a single 128x128x32 tile pipeline is mostly padding
   const bool worthwhile = (long long)m * n >= 64 * 64 && k >= 32;
   if (variant == 2 || (variant == 0 && tc_ok && worthwhile)) {
-    int st = sgemm_tcgen05(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    int st = sgemm_tcgen05(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri);
     if (st != RTAT_B200_STATUS_NOT_SUPPORTED || variant == 2) return st;
   }
-  return sgemm_simt(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  return sgemm_simt(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri);
 }
 
 }  // namespace rtat_b200

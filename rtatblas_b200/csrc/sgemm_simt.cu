@@ -11,12 +11,21 @@ namespace rtat_b200 {
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_simt_kernel(int m, int n, int k, float alpha, const float *__restrict__ A, int lda,
-                  const float *__restrict__ B, int ldb, float beta, float *C, int ldc, int tiles_m) {
+                  const float *__restrict__ B, int ldb, float beta, float *C, int ldc, int tiles_m, int tri) {
   constexpr int BM = 128, BN = 128, BK = 8;
   __shared__ float sA[2][BK][BM + 4];
   __shared__ float sB[2][BK][BN + 4];
   const int tid = threadIdx.x;
-  const int m0 = (blockIdx.x % tiles_m) * BM, n0 = (blockIdx.x / tiles_m) * BN;
+  int m0 = (blockIdx.x % tiles_m) * BM, n0 = (blockIdx.x / tiles_m) * BN;
+  if (tri) {  // SSYRK: blockIdx.x = i (i + 1) / 2 + j enumerates the tiles of the triangle, i >= j
+    const int t = blockIdx.x;
+    int i = int((__fsqrt_rn(8.0f * float(t) + 1.0f) - 1.0f) * 0.5f);
+    while ((long long)i * (i + 1) / 2 > t) i--;
+    while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
+    const int j = t - int((long long)i * (i + 1) / 2);
+    m0 = (tri == 1 ? i : j) * BM;
+    n0 = (tri == 1 ? j : i) * BN;
+  }
   const int tx = tid % 16, ty = tid / 16;  // thread owns rows tx*4..+3 and 64+tx*4..+3, cols likewise with ty
 
   // loader mapping: each thread fetches 4 elements of A and 4 of B per k-tile
@@ -87,7 +96,7 @@ sgemm_simt_kernel(int m, int n, int k, float alpha, const float *__restrict__ A,
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       int row = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
-      if (row < m) {
+      if (row < m && !(tri == 1 && row < col) && !(tri == 2 && row > col)) {
         float v = alpha * acc[i][j];
         if (beta != 0.f) v += beta * C[(size_t)col * ldc + row];
         C[(size_t)col * ldc + row] = v;
@@ -97,17 +106,18 @@ sgemm_simt_kernel(int m, int n, int k, float alpha, const float *__restrict__ A,
 }
 
 int sgemm_simt(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
-               const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc) {
+               const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri) {
   int tiles_m = (m + 127) / 128, tiles_n = (n + 127) / 128;
   long long tiles = (long long)tiles_m * tiles_n;
+  if (tri) tiles = (long long)tiles_m * (tiles_m + 1) / 2;
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
   dim3 grid((unsigned)tiles), block(256);
-  if (!ta && !tb) sgemm_simt_kernel<false, false><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m);
-  else if (ta && !tb) sgemm_simt_kernel<true, false><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m);
-  else if (!ta && tb) sgemm_simt_kernel<false, true><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m);
-  else sgemm_simt_kernel<true, true><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m);
-  return check_launch(h, "sgemm_simt_fp32_128x128x8");
+  if (!ta && !tb) sgemm_simt_kernel<false, false><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tri);
+  else if (ta && !tb) sgemm_simt_kernel<true, false><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tri);
+  else if (!ta && tb) sgemm_simt_kernel<false, true><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tri);
+  else sgemm_simt_kernel<true, true><<<grid, block, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tri);
+  return check_launch(h, tri ? "ssyrk_simt_fp32_128x128x8" : "sgemm_simt_fp32_128x128x8");
 }
 
 }  // namespace rtat_b200

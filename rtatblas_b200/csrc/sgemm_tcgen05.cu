@@ -58,7 +58,23 @@ struct Params {
   int ldc;
   float alpha, beta;
   int tiles_m, tiles_n, num_tiles, kb;  // kb = ceil(k / BK)
+  int tri;  // SSYRK: 1 = lower / 2 = upper triangle only (tiles enumerate the triangle, diagonal tiles are masked)
 };
+
+// Origin of tile `tile`: column-major over the tile grid for GEMM; for SYRK tile t = i (i + 1) / 2 + j, i >= j.
+__device__ __forceinline__ void tile_origin(const Params &p, int tile, int &m0, int &n0) {
+  if (p.tri) {
+    int i = int((__fsqrt_rn(8.0f * float(tile) + 1.0f) - 1.0f) * 0.5f);
+    while ((long long)i * (i + 1) / 2 > tile) i--;
+    while ((long long)(i + 1) * (i + 2) / 2 <= tile) i++;
+    const int j = tile - int((long long)i * (i + 1) / 2);
+    m0 = (p.tri == 1 ? i : j) * BM;
+    n0 = (p.tri == 1 ? j : i) * BN;
+  } else {
+    m0 = (tile % p.tiles_m) * BM;
+    n0 = (tile / p.tiles_m) * BN;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
@@ -185,7 +201,8 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+        int m0, n0;
+      tile_origin(p, tile, m0, n0);
         for (int kb = 0; kb < p.kb; kb++) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t full = full0 + 8 * stage;
@@ -328,7 +345,8 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
     };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+      int m0, n0;
+      tile_origin(p, tile, m0, n0);
       float sum[BN];  // this thread's row of the tile: FP32 registers, round-to-nearest adds
 #pragma unroll
       for (int j = 0; j < BN; j++) sum[j] = 0.f;
@@ -353,7 +371,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < BN; j++) {
           const int col = n0 + j;
-          if (col < p.n) {
+          if (col < p.n && !(p.tri == 1 && row < col) && !(p.tri == 2 && row > col)) {
             float *dst = p.C + (size_t)col * p.ldc + row;
             float v = alpha * sum[j];
             if (beta != 0.f) v += beta * *dst;
@@ -415,6 +433,7 @@ static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, 
   }
   int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, mbs, p);
+  if (p.tri) return check_launch(h, PRESPLIT ? "ssyrk_tcgen05_3xtf32_128x128x32_presplitB" : "ssyrk_tcgen05_3xtf32_128x128x32", PRESPLIT ? 2 : 1);
   return check_launch(h, PRESPLIT ? "sgemm_tcgen05_3xtf32_128x128x32_presplitB" : "sgemm_tcgen05_3xtf32_128x128x32", PRESPLIT ? 2 : 1);
 }
 
@@ -440,13 +459,17 @@ bool sgemm_tcgen05_supported(const rtat_b200_context *h, int, int, int m, int n,
 }
 
 int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha, const float *A, int lda, const float *B,
-                  int ldb, float beta, float *C, int ldc) {
+                  int ldb, float beta, float *C, int ldc, int tri) {
   using namespace tc;
   const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
-  Params p{m, n, k, C, ldc, alpha, beta, 0, 0, 0, 0};
+  Params p{m, n, k, C, ldc, alpha, beta, 0, 0, 0, 0, tri};
   p.tiles_m = (m + BM - 1) / BM;
   p.tiles_n = (n + BN - 1) / BN;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
+  if (tri) {
+    if (m != n) return RTAT_B200_STATUS_INVALID_VALUE;
+    tiles = (long long)p.tiles_m * (p.tiles_m + 1) / 2;
+  }
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   p.num_tiles = (int)tiles;
   p.kb = (k + BK - 1) / BK;

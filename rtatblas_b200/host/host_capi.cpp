@@ -15,6 +15,18 @@ struct Planner_Base {
   virtual int gemm(rtat_b200_handle_t h, int ta, int tb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B,
                    int ldb, const void *beta, void *C, int ldc, void *ws, size_t ws_bytes, const char *forced, char *plan_out) = 0;
   virtual long long workspace(int ta, int tb, int m, int n, int k, int lda, int ldb, int ldc, const char *plan) = 0;
+  virtual int syrk(rtat_b200_handle_t, int, int, int, int, const void *, const void *, int, const void *, void *, int, void *, size_t,
+                   const char *, char *) {
+    throw std::runtime_error("this planner is not a syrk planner");
+  }
+  virtual long long syrk_workspace(int, int, int, int, int, int, const char *) { throw std::runtime_error("this planner is not a syrk planner"); }
+  virtual int trsm(rtat_b200_handle_t, int, int, int, int, int, int, const void *, const void *, int, void *, int, void *, size_t, const char *,
+                   char *) {
+    throw std::runtime_error("this planner is not a trsm planner");
+  }
+  virtual long long trsm_workspace(int, int, int, int, int, int, int, int, const char *) {
+    throw std::runtime_error("this planner is not a trsm planner");
+  }
   virtual std::string statistics() = 0;
   virtual std::string save_plans() = 0;
   virtual long long load_plans(const char *text) = 0;
@@ -23,8 +35,9 @@ struct Planner_Base {
   virtual std::string plan_name(int i) = 0;
 };
 
-template <typename T, typename Exec, typename Opts>
-struct Planner_Impl : Planner_Base {
+// what every method's planner shares: plan parsing, statistics, the plan cache
+template <typename Exec, typename Opts>
+struct Planner_Common : Planner_Base {
   Planning_System<Exec> planner;
 
   static Opts parse(const char *plan) {
@@ -33,6 +46,73 @@ struct Planner_Impl : Planner_Base {
     if (!(in >> o)) throw std::runtime_error(std::string("bad plan string ") + plan);
     return o;
   }
+  template <typename Inputs, typename Key>
+  int run(rtat_b200_handle_t h, Inputs in, Key key, void *ws, size_t ws_bytes, const char *forced, char *plan_out) {
+    Opts plan = forced && *forced ? parse(forced) : planner.create_plan(key);
+    gpu::Stream_t raw = nullptr;
+    gpu::blasGetStream(h, &raw);
+    planner.execute(in, plan, Workspace((char *)ws, ws_bytes), Stream(raw));
+    if (plan_out) std::strcpy(plan_out, std::string(plan).c_str());
+    return 0;
+  }
+  int gemm(rtat_b200_handle_t, int, int, int, int, int, const void *, const void *, int, const void *, int, const void *, void *, int, void *,
+           size_t, const char *, char *) override {
+    throw std::runtime_error("this planner is not a gemm planner");
+  }
+  long long workspace(int, int, int, int, int, int, int, int, const char *) override { throw std::runtime_error("this planner is not a gemm planner"); }
+  std::string statistics() override { return planner.make_statistics().json().dump(1); }
+  std::string save_plans() override { return planner.save_plans().dump(1); }
+  long long load_plans(const char *text) override { return (long long)planner.load_plans(Json::parse(text)); }
+  void set_converge(int n) override { planner.set_tests_until_converge((size_t)n); }
+  int num_plans() override { return (int)Opts::enumerate().size(); }
+  std::string plan_name(int i) override { return std::string(Opts::enumerate().at((size_t)i)); }
+};
+
+template <typename T>
+struct Syrk_Planner : Planner_Common<SYRK_Executor<T>, SYRK_Options> {
+  static SYRK_Inputs<T> inputs(rtat_b200_handle_t h, int uplo, int trans, int n, int k, T alpha, const void *A, int lda, T beta, void *C, int ldc) {
+    const size_t ar = trans ? k : n, ac = trans ? n : k;
+    Matrix<T> Am(Workspace((T *)A, (size_t)lda * ac), ar, ac, lda), Cm(Workspace((T *)C, (size_t)ldc * n), n, n, ldc);
+    return SYRK_Inputs<T>(h, uplo == RTAT_B200_FILL_LOWER ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER,
+                          trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, Am, Cm, alpha, beta);
+  }
+  int syrk(rtat_b200_handle_t h, int uplo, int trans, int n, int k, const void *alpha, const void *A, int lda, const void *beta, void *C, int ldc,
+           void *ws, size_t ws_bytes, const char *forced, char *plan_out) override {
+    auto in = inputs(h, uplo, trans, n, k, *(const T *)alpha, A, lda, *(const T *)beta, C, ldc);
+    return this->run(h, in, SYRK_Key(in), ws, ws_bytes, forced, plan_out);
+  }
+  long long syrk_workspace(int uplo, int trans, int n, int k, int lda, int ldc, const char *plan) override {
+    auto in = inputs(nullptr, uplo, trans, n, k, T(1), nullptr, lda, T(0), nullptr, ldc);
+    return (long long)this->planner.calculate_workspace(in, this->parse(plan));
+  }
+};
+
+template <typename T>
+struct Trsm_Planner : Planner_Common<TRSM_Executor<T>, TRSM_Options> {
+  static TRSM_Inputs<T> inputs(rtat_b200_handle_t h, int side, int uplo, int trans, int diag, int m, int n, T alpha, const void *A, int lda,
+                               void *B, int ldb) {
+    const size_t na = side == RTAT_B200_SIDE_LEFT ? m : n;
+    Matrix<T> Am(Workspace((T *)A, (size_t)lda * na), na, na, lda), Bm(Workspace((T *)B, (size_t)ldb * n), m, n, ldb);
+    return TRSM_Inputs<T>(h, side == RTAT_B200_SIDE_LEFT ? gpu::BLAS_SIDE_LEFT : gpu::BLAS_SIDE_RIGHT,
+                          uplo == RTAT_B200_FILL_LOWER ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER,
+                          trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, diag == RTAT_B200_DIAG_UNIT ? gpu::BLAS_DIAG_UNIT : gpu::BLAS_DIAG_NON_UNIT, Am,
+                          Bm, alpha);
+  }
+  int trsm(rtat_b200_handle_t h, int side, int uplo, int trans, int diag, int m, int n, const void *alpha, const void *A, int lda, void *B,
+           int ldb, void *ws, size_t ws_bytes, const char *forced, char *plan_out) override {
+    auto in = inputs(h, side, uplo, trans, diag, m, n, *(const T *)alpha, A, lda, B, ldb);
+    return this->run(h, in, TRSM_Key(in), ws, ws_bytes, forced, plan_out);
+  }
+  long long trsm_workspace(int side, int uplo, int trans, int diag, int m, int n, int lda, int ldb, const char *plan) override {
+    auto in = inputs(nullptr, side, uplo, trans, diag, m, n, T(1), nullptr, lda, nullptr, ldb);
+    return (long long)this->planner.calculate_workspace(in, this->parse(plan));
+  }
+};
+
+template <typename T, typename Exec, typename Opts>
+struct Planner_Impl : Planner_Common<Exec, Opts> {
+  using Planner_Common<Exec, Opts>::planner;
+  using Planner_Common<Exec, Opts>::parse;
   static GEMM_Inputs<T> inputs(rtat_b200_handle_t h, int ta, int tb, int m, int n, int k, T alpha, const void *A, int lda, const void *B,
                                int ldb, T beta, void *C, int ldc) {
     const size_t ac = ta ? m : k, bc = tb ? k : n;
@@ -44,23 +124,12 @@ struct Planner_Impl : Planner_Base {
   int gemm(rtat_b200_handle_t h, int ta, int tb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
            const void *beta, void *C, int ldc, void *ws, size_t ws_bytes, const char *forced, char *plan_out) override {
     auto in = inputs(h, ta, tb, m, n, k, *(const T *)alpha, A, lda, B, ldb, *(const T *)beta, C, ldc);
-    Opts plan = forced && *forced ? parse(forced) : planner.create_plan(GEMM_Key(in));
-    gpu::Stream_t raw = nullptr;
-    gpu::blasGetStream(h, &raw);
-    planner.execute(in, plan, Workspace((char *)ws, ws_bytes), Stream(raw));
-    if (plan_out) std::strcpy(plan_out, std::string(plan).c_str());
-    return 0;
+    return this->run(h, in, GEMM_Key(in), ws, ws_bytes, forced, plan_out);
   }
   long long workspace(int ta, int tb, int m, int n, int k, int lda, int ldb, int ldc, const char *plan) override {
     auto in = inputs(nullptr, ta, tb, m, n, k, T(1), nullptr, lda, nullptr, ldb, T(0), nullptr, ldc);
     return (long long)planner.calculate_workspace(in, parse(plan));
   }
-  std::string statistics() override { return planner.make_statistics().json().dump(1); }
-  std::string save_plans() override { return planner.save_plans().dump(1); }
-  long long load_plans(const char *text) override { return (long long)planner.load_plans(Json::parse(text)); }
-  void set_converge(int n) override { planner.set_tests_until_converge((size_t)n); }
-  int num_plans() override { return (int)Opts::enumerate().size(); }
-  std::string plan_name(int i) override { return std::string(Opts::enumerate().at((size_t)i)); }
 };
 
 thread_local std::string last_error;
@@ -97,6 +166,10 @@ rtat_host_planner_t rtat_host_planner_create(const char *method, const char *dat
     else if (m == "gemm" && d == "float") p = new Planner_Impl<float, GEMM_Executor<float>, GEMM_Options>();
     else if (m == "gemm_pad" && d == "double") p = new Planner_Impl<double, GEMM_Executor_Pad<double>, GEMM_Options_Pad>();
     else if (m == "gemm_pad" && d == "float") p = new Planner_Impl<float, GEMM_Executor_Pad<float>, GEMM_Options_Pad>();
+    else if (m == "syrk" && d == "double") p = new Syrk_Planner<double>();
+    else if (m == "syrk" && d == "float") p = new Syrk_Planner<float>();
+    else if (m == "trsm" && d == "double") p = new Trsm_Planner<double>();
+    else if (m == "trsm" && d == "float") p = new Trsm_Planner<float>();
     else throw std::runtime_error("unknown method/data_type: " + m + "/" + d);
     return 0;
   });
@@ -121,6 +194,34 @@ long long rtat_host_planner_workspace(rtat_host_planner_t p, int transa, int tra
     out = static_cast<Planner_Base *>(p)->workspace(transa, transb, m, n, k, lda, ldb, ldc, plan);
     return 0;
   });
+  return out;
+}
+int rtat_host_planner_syrk(rtat_host_planner_t p, rtat_b200_handle_t h, int uplo, int trans, int n, int k, const void *alpha, const void *A,
+                           int lda, const void *beta, void *C, int ldc, void *workspace, size_t workspace_bytes, const char *forced_plan,
+                           char *plan_out) {
+  if (!p || !h) return -1;
+  return guarded([&] {
+    return static_cast<Planner_Base *>(p)->syrk(h, uplo, trans, n, k, alpha, A, lda, beta, C, ldc, workspace, workspace_bytes, forced_plan, plan_out);
+  });
+}
+long long rtat_host_planner_syrk_workspace(rtat_host_planner_t p, int uplo, int trans, int n, int k, int lda, int ldc, const char *plan) {
+  long long out = -1;
+  if (p) guarded([&] { out = static_cast<Planner_Base *>(p)->syrk_workspace(uplo, trans, n, k, lda, ldc, plan); return 0; });
+  return out;
+}
+int rtat_host_planner_trsm(rtat_host_planner_t p, rtat_b200_handle_t h, int side, int uplo, int trans, int diag, int m, int n,
+                           const void *alpha, const void *A, int lda, void *B, int ldb, void *workspace, size_t workspace_bytes,
+                           const char *forced_plan, char *plan_out) {
+  if (!p || !h) return -1;
+  return guarded([&] {
+    return static_cast<Planner_Base *>(p)->trsm(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, workspace, workspace_bytes, forced_plan,
+                                                plan_out);
+  });
+}
+long long rtat_host_planner_trsm_workspace(rtat_host_planner_t p, int side, int uplo, int trans, int diag, int m, int n, int lda, int ldb,
+                                           const char *plan) {
+  long long out = -1;
+  if (p) guarded([&] { out = static_cast<Planner_Base *>(p)->trsm_workspace(side, uplo, trans, diag, m, n, lda, ldb, plan); return 0; });
   return out;
 }
 char *rtat_host_planner_statistics(rtat_host_planner_t p) {

@@ -16,6 +16,8 @@ static Json run(const Input_File &file) {
 
 static Json dispatch(const Input_File &file) {
   const bool dbl = file.data_type.val == Data_Type::DOUBLE;
+  if (file.method.val == Method::TRSM) return dbl ? run<TRSM_Executor<double>>(file) : run<TRSM_Executor<float>>(file);
+  if (file.method.val == Method::SYRK) return dbl ? run<SYRK_Executor<double>>(file) : run<SYRK_Executor<float>>(file);
   if (file.method.val == Method::GEMM) return dbl ? run<GEMM_Executor<double>>(file) : run<GEMM_Executor<float>>(file);
   return dbl ? run<GEMM_Executor_Pad<double>>(file) : run<GEMM_Executor_Pad<float>>(file);
 }

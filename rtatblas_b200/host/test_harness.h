@@ -26,14 +26,15 @@ struct Run_Type {
 };
 
 struct Method {
-  enum _Method { GEMM, GEMM_PAD } val;
+  enum _Method { GEMM, GEMM_PAD, SYRK, TRSM } val;
   Method(const std::string &s) {
     if (s == "gemm") val = GEMM;
     else if (s == "gemm_pad") val = GEMM_PAD;
-    else if (s == "syrk" || s == "trsm") throw std::runtime_error("method " + s + " is outside the GEMM execution path this back end covers");
+    else if (s == "syrk") val = SYRK;
+    else if (s == "trsm") val = TRSM;
     else throw std::runtime_error("Invalid method: " + s);
   }
-  operator std::string() const { return val == GEMM ? "gemm" : "gemm_pad"; }
+  operator std::string() const { return val == GEMM ? "gemm" : val == GEMM_PAD ? "gemm_pad" : val == SYRK ? "syrk" : "trsm"; }
 };
 
 struct Data_Type {
@@ -167,6 +168,26 @@ class Test_Harness {
     MatrixDims Cd(key.m, key.n, key.m);
     auto ms = resources.allocate_matrices<T>({Ad, Bd, Cd});
     return GEMM_Inputs<T>(resources.handle, key.transa, key.transb, ms[0], ms[1], ms[2], T(1), T(0));
+  }
+
+  // tight leading dimensions, alpha = 1, beta = 0 (reference test_harness.h:264-278)
+  template <typename T>
+  SYRK_Inputs<T> form_input(SYRK_Key key) {
+    const bool an = key.trans == gpu::BLAS_OP_N;
+    MatrixDims Ad(an ? key.n : key.k, an ? key.k : key.n, an ? key.n : key.k);
+    MatrixDims Cd(key.n, key.n, key.n);
+    auto ms = resources.allocate_matrices<T>({Ad, Cd});
+    return SYRK_Inputs<T>(resources.handle, key.uplo, key.trans, ms[0], ms[1], T(1), T(0));
+  }
+
+  // tight leading dimensions, alpha = 1 (reference test_harness.h:250-262).  The fill is U(0,1] like the
+  // reference's; it does not condition A, so timings are meaningful and values are not.
+  template <typename T>
+  TRSM_Inputs<T> form_input(TRSM_Key key) {
+    const size_t na = key.side == gpu::BLAS_SIDE_LEFT ? key.m : key.n;
+    MatrixDims Ad(na, na, na), Bd(key.m, key.n, key.m);
+    auto ms = resources.allocate_matrices<T>({Ad, Bd});
+    return TRSM_Inputs<T>(resources.handle, key.side, key.uplo, key.trans, key.diag, ms[0], ms[1], T(1));
   }
 };
 

@@ -82,16 +82,22 @@ inline blasStatus_t blasSgeam(blasHandle_t h, blasOperation_t ta, blasOperation_
                               const float *A, int lda, const float *beta, const float *B, int ldb, float *C, int ldc) {
   return rtat_b200_sgeam(h, ta, tb, m, n, alpha, A, lda, beta, B, ldb, C, ldc);
 }
-// TRSM / SYRK are outside this back end's scope: the names exist so that code
-// written against the reference table still compiles, and report NOT_SUPPORTED when called.
-template <typename... Args>
-inline blasStatus_t blasDtrsm(Args &&...) { return RTAT_B200_STATUS_NOT_SUPPORTED; }
-template <typename... Args>
-inline blasStatus_t blasStrsm(Args &&...) { return RTAT_B200_STATUS_NOT_SUPPORTED; }
-template <typename... Args>
-inline blasStatus_t blasDsyrk(Args &&...) { return RTAT_B200_STATUS_NOT_SUPPORTED; }
-template <typename... Args>
-inline blasStatus_t blasSsyrk(Args &&...) { return RTAT_B200_STATUS_NOT_SUPPORTED; }
+inline blasStatus_t blasDsyrk(blasHandle_t h, blasFillMode_t uplo, blasOperation_t trans, int n, int k, const double *alpha,
+                              const double *A, int lda, const double *beta, double *C, int ldc) {
+  return rtat_b200_dsyrk(h, uplo, trans, n, k, alpha, A, lda, beta, C, ldc);
+}
+inline blasStatus_t blasSsyrk(blasHandle_t h, blasFillMode_t uplo, blasOperation_t trans, int n, int k, const float *alpha,
+                              const float *A, int lda, const float *beta, float *C, int ldc) {
+  return rtat_b200_ssyrk(h, uplo, trans, n, k, alpha, A, lda, beta, C, ldc);
+}
+inline blasStatus_t blasDtrsm(blasHandle_t h, blasSideMode_t side, blasFillMode_t uplo, blasOperation_t trans, blasDiagType_t diag, int m,
+                              int n, const double *alpha, const double *A, int lda, double *B, int ldb) {
+  return rtat_b200_dtrsm(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb);
+}
+inline blasStatus_t blasStrsm(blasHandle_t h, blasSideMode_t side, blasFillMode_t uplo, blasOperation_t trans, blasDiagType_t diag, int m,
+                              int n, const float *alpha, const float *A, int lda, float *B, int ldb) {
+  return rtat_b200_strsm(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb);
+}
 
 }  // namespace gpu
 

@@ -9,6 +9,12 @@
 //   MatrixAccumulate  in place  B = alpha*op(A) + beta*B                                   -> geam
 //   MatrixMult      in place  C = alpha*op(A)*op(B) + beta*C                               -> gemm
 //   MatrixMultAlloc fresh padded  C = alpha*op(A)*op(B)                                    -> gemm
+// and by the SYRK plans (reference syrk.cpp:72-104):
+//   MatrixSyrk      in place  C(tri) = alpha*op(A)*op(A)^T + beta*C(tri)                   -> syrk
+//   MatrixSyrkAlloc fresh zeroed n x n buffer, then its triangle = alpha*op(A)*op(A)^T     -> geam + syrk
+// and by the TRSM plans (reference trsm.cpp:72-113):
+//   MatrixTrs       in place  B = alpha * op(A)^-1 B  or  alpha * B op(A)^-1               -> trsm
+//   MatrixTrsAlloc  same, but B is an operand that was just materialised in this node's own buffer
 // Scratch is carved front-to-back in operand order, so the byte layout of a plan's workspace is the
 // reference's (matrixop.h:192-210); tests/ pin it against the oracle.
 #pragma once
@@ -47,6 +53,35 @@ inline gpu::blasStatus_t gpuTgeam(gpu::blasHandle_t handle, bool transa, bool tr
     return gpu::blasDgeam(handle, opa, opb, m, n, &alpha, A.ptr(), (int)A.dims().ld, &beta, B.ptr(), (int)B.dims().ld, C.ptr(), (int)C.dims().ld);
   else
     return gpu::blasSgeam(handle, opa, opb, m, n, &alpha, A.ptr(), (int)A.dims().ld, &beta, B.ptr(), (int)B.dims().ld, C.ptr(), (int)C.dims().ld);
+}
+
+// C(tri) = alpha*op(A)*op(A)^T + beta*C(tri); n from C, k from A (reference matrixop.h:48-76)
+template <typename T>
+inline gpu::blasStatus_t gpuTsyrk(gpu::blasHandle_t handle, bool lower, bool trans, Matrix<T> A, Matrix<T> C, const T alpha, const T beta) {
+  static_assert(std::is_same_v<T, double> || std::is_same_v<T, float>, "SYRK is only double and float");
+  const int n = (int)C.dims().n, k = (int)(trans ? A.dims().m : A.dims().n);
+  const auto uplo = lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER;
+  const auto op = trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N;
+  if constexpr (std::is_same_v<T, double>)
+    return gpu::blasDsyrk(handle, uplo, op, n, k, &alpha, A.ptr(), (int)A.dims().ld, &beta, C.ptr(), (int)C.dims().ld);
+  else
+    return gpu::blasSsyrk(handle, uplo, op, n, k, &alpha, A.ptr(), (int)A.dims().ld, &beta, C.ptr(), (int)C.dims().ld);
+}
+
+// op(A) X = alpha B or X op(A) = alpha B, X over B; m, n from B (reference matrixop.h:78-109)
+template <typename T>
+inline gpu::blasStatus_t gpuTtrsm(gpu::blasHandle_t handle, bool side_left, bool lower, bool trans, bool unit_diag, Matrix<T> A, Matrix<T> B,
+                                  const T alpha) {
+  static_assert(std::is_same_v<T, double> || std::is_same_v<T, float>, "TRSM is only double and float");
+  const int m = (int)B.dims().m, n = (int)B.dims().n;
+  const auto side = side_left ? gpu::BLAS_SIDE_LEFT : gpu::BLAS_SIDE_RIGHT;
+  const auto uplo = lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER;
+  const auto op = trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N;
+  const auto diag = unit_diag ? gpu::BLAS_DIAG_UNIT : gpu::BLAS_DIAG_NON_UNIT;
+  if constexpr (std::is_same_v<T, double>)
+    return gpu::blasDtrsm(handle, side, uplo, op, diag, m, n, &alpha, A.ptr(), (int)A.dims().ld, B.ptr(), (int)B.dims().ld);
+  else
+    return gpu::blasStrsm(handle, side, uplo, op, diag, m, n, &alpha, A.ptr(), (int)A.dims().ld, B.ptr(), (int)B.dims().ld);
 }
 
 inline size_t round_up_to(size_t x, size_t pad) { return ((x + pad - 1) / pad) * pad; }
@@ -248,6 +283,102 @@ class MatrixMultAlloc : public MatrixOp<T> {
     auto ms = this->compute_operands(handle, out_space, scratch_space);
     Matrix<T> C(out_space, dims());
     blas_status_check(gpuTgemm<T>(handle, transa, transb, ms[0], ms[1], C, alpha, T(0)), "MatrixMultAlloc: gemm");
+    return C;
+  }
+};
+
+// Triangular solve in place of operand 1.  OWNS_OUTPUT = false: B is an existing matrix (MatrixTrs, reference
+// matrixop.h:442-486).  OWNS_OUTPUT = true: B is produced by operand 1 directly into this node's output buffer,
+// whose footprint this node therefore reports (MatrixTrsAlloc, matrixop.h:488-534).
+template <typename T, bool OWNS_OUTPUT>
+class MatrixTrsBase : public MatrixOp<T> {
+ protected:
+  bool side_left, lower, trans, unit_diag;
+  T alpha;
+  size_t pad;
+
+ public:
+  MatrixTrsBase(std::unique_ptr<MatrixOp<T>> Aop, std::unique_ptr<MatrixOp<T>> Bop, bool side_left, bool lower, bool trans, bool unit_diag,
+                T alpha, size_t pad = 1)
+      : MatrixOp<T>({}, 1), side_left(side_left), lower(lower), trans(trans), unit_diag(unit_diag), alpha(alpha), pad(pad) {
+    const MatrixDims a = Aop->dims(), b = Bop->dims();
+    if (a.m != a.n || (side_left ? b.m : b.n) != a.m) {
+      std::cout << "Bad matrix trs, mA=" << a.m << " nA=" << a.n << " mB=" << b.m << " nB=" << b.n << " " << (side_left ? "LEFT" : "RIGHT")
+                << std::endl;
+      std::terminate();  // the reference's bare `throw;` (matrixop.h:459, :508)
+    }
+    this->operands.push_back(std::move(Aop));
+    this->operands.push_back(std::move(Bop));
+  }
+  MatrixDims dims() const override {
+    const MatrixDims b = this->operands[1]->dims();
+    return OWNS_OUTPUT ? MatrixDims(b.m, b.n, round_up_to(b.m, pad)) : b;
+  }
+  size_t output_space_req() const override { return OWNS_OUTPUT ? dims().footprint() : 0; }
+  Matrix<T> execute(gpu::blasHandle_t handle, Workspace out_space, Workspace scratch_space) override {
+    auto ms = this->compute_operands(handle, out_space, scratch_space);
+    blas_status_check(gpuTtrsm<T>(handle, side_left, lower, trans, unit_diag, ms[0], ms[1], alpha), "MatrixTrs: trsm");
+    return ms[1];
+  }
+};
+template <typename T>
+using MatrixTrs = MatrixTrsBase<T, false>;
+template <typename T>
+using MatrixTrsAlloc = MatrixTrsBase<T, true>;
+
+// in place: C(tri) = alpha*op(A)*op(A)^T + beta*C(tri)   (C is operand 1 and the output)
+template <typename T>
+class MatrixSyrk : public MatrixOp<T> {
+ protected:
+  bool lower, trans;
+  T alpha, beta;
+
+ public:
+  MatrixSyrk(std::unique_ptr<MatrixOp<T>> Aop, std::unique_ptr<MatrixOp<T>> Cop, bool lower, bool trans, T alpha, T beta)
+      : MatrixOp<T>({}, 1), lower(lower), trans(trans), alpha(alpha), beta(beta) {
+    const MatrixDims a = Aop->dims(), c = Cop->dims();
+    if ((trans ? a.n : a.m) != c.n || c.m != c.n) {
+      std::cout << "Bad matrix syrk, mA=" << a.m << " nA=" << a.n << " mC=" << c.m << " nC=" << c.n << std::endl;
+      std::terminate();  // the reference's bare `throw;` (matrixop.h:552)
+    }
+    this->operands.push_back(std::move(Aop));
+    this->operands.push_back(std::move(Cop));
+  }
+  MatrixDims dims() const override { return this->operands[1]->dims(); }
+  size_t output_space_req() const override { return 0; }
+  Matrix<T> execute(gpu::blasHandle_t handle, Workspace out_space, Workspace scratch_space) override {
+    auto ms = this->compute_operands(handle, out_space, scratch_space);
+    blas_status_check(gpuTsyrk<T>(handle, lower, trans, ms[0], ms[1], alpha, beta), "MatrixSyrk: syrk");
+    return ms[1];
+  }
+};
+
+// fresh n x n buffer, zero-filled, whose `lower`/upper triangle then receives alpha*op(A)*op(A)^T.  The zero
+// fill matters: the caller folds the WHOLE buffer back with a transposed accumulate (syrk.cpp:92-97).
+template <typename T>
+class MatrixSyrkAlloc : public MatrixOp<T> {
+ protected:
+  bool lower, trans;
+  T alpha;
+  size_t pad;
+
+ public:
+  MatrixSyrkAlloc(std::unique_ptr<MatrixOp<T>> Aop, bool lower, bool trans, T alpha, size_t pad = 1)
+      : MatrixOp<T>({}), lower(lower), trans(trans), alpha(alpha), pad(pad) {
+    this->operands.push_back(std::move(Aop));
+  }
+  MatrixDims dims() const override {
+    const MatrixDims a = this->operands[0]->dims();
+    const size_t n = trans ? a.n : a.m;
+    return MatrixDims(n, n, round_up_to(n, pad));
+  }
+  size_t output_space_req() const override { return dims().footprint(); }
+  Matrix<T> execute(gpu::blasHandle_t handle, Workspace out_space, Workspace scratch_space) override {
+    auto ms = this->compute_operands(handle, out_space, scratch_space);
+    Matrix<T> C(out_space, dims());
+    // alpha = beta = 0: neither operand is read, C is just cleared (reference matrixop.h:612)
+    blas_status_check(gpuTgeam<T>(handle, false, false, C, C, C, T(0), T(0)), "MatrixSyrkAlloc: geam");
+    blas_status_check(gpuTsyrk<T>(handle, lower, trans, ms[0], C, alpha, T(0)), "MatrixSyrkAlloc: syrk");
     return C;
   }
 };

@@ -102,6 +102,106 @@ TEST(GEMM_Executor_Test, Insufficient_Workspace_Throws) {
   ASSERT_THROWS(exec.execute(in, GEMM_Options(BLAS_Op::TRANS, BLAS_Op::NOTRANS, BLAS_Op::NOTRANS), Workspace(), f.s));
 }
 
+// ---- tests/executor_test.cpp:132-225: B := op(A) X (or X op(A)) by GEMM, solve it back, compare with X --------
+template <typename T>
+static void trsm_executor_correctness(int m, int n, T tol) {
+  BLAS_Fixture f;
+  TRSM_Executor<T> trsm_exec;
+  GEMM_Executor<T> gemm_exec;
+  for (bool side_left : {false, true})
+    for (bool lower : {false, true})
+      for (bool unit_diag : {false, true})
+        for (bool trans : {false, true})
+          for (auto &opts : TRSM_Options::enumerate()) {
+            const int na = side_left ? m : n;
+            TestMatrix<T> A(na, na), X(m, n), B(m, n);
+            // keep only the `lower`/upper triangle, make it well conditioned (the reference adds m+1 to the
+            // diagonal, or divides the off-diagonals of a unit-diagonal A by m: executor_test.cpp:146-176)
+            for (int c = 0; c < na; c++)
+              for (int r = 0; r < na; r++) {
+                T &a = A.host[(size_t)c * A.ld + r];
+                if (lower ? r < c : r > c) a = 0;
+                else if (r == c) a = unit_diag ? T(1) : a + T(na + 1);
+                else if (unit_diag) a /= T(na);
+              }
+            A.upload();
+            if (side_left) {
+              GEMM_Inputs<T> in(f.handle, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, gpu::BLAS_OP_N, A, X, B, T(1), T(0));
+              gemm_exec.execute(in, GEMM_Options(), Workspace(), f.s);
+            } else {
+              GEMM_Inputs<T> in(f.handle, gpu::BLAS_OP_N, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, X, A, B, T(1), T(0));
+              gemm_exec.execute(in, GEMM_Options(), Workspace(), f.s);
+            }
+            // poison the triangle TRSM must not read (and the diagonal of a unit-diagonal A)
+            for (int c = 0; c < na; c++)
+              for (int r = 0; r < na; r++)
+                if ((lower ? r < c : r > c) || (unit_diag && r == c)) A.host[(size_t)c * A.ld + r] = NAN;
+            f.s.synchronize();
+            A.upload();
+            TRSM_Inputs<T> in(f.handle, side_left ? gpu::BLAS_SIDE_LEFT : gpu::BLAS_SIDE_RIGHT,
+                              lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N,
+                              unit_diag ? gpu::BLAS_DIAG_UNIT : gpu::BLAS_DIAG_NON_UNIT, A, B, T(1));
+            ManagedWorkspace space(trsm_exec.calculate_workspace(in, opts));
+            trsm_exec.execute(in, opts, space, f.s);
+            f.s.synchronize();
+            B.download();
+            double delta = 0;
+            for (int c = 0; c < n; c++)
+              for (int r = 0; r < m; r++) delta = std::max(delta, (double)std::abs(B.host[(size_t)c * B.ld + r] - X.host[(size_t)c * X.ld + r]));
+            EXPECT_TRUE(delta < tol);
+            if (!(delta < tol)) std::cout << "delta=" << delta << " plan=" << std::string(opts) << " key=" << std::string(TRSM_Key(in)) << std::endl;
+          }
+}
+TEST(TRSM_Executor_Test, TRSM_Correctness_Double) { trsm_executor_correctness<double>(435, 527, 1e-10); }
+TEST(TRSM_Executor_Test, TRSM_Correctness_Single) { trsm_executor_correctness<float>(131, 97, 1e-3f); }
+
+// ---- tests/executor_test.cpp:227-290: C := op(A)op(A)^T by GEMM, C -= the same by SYRK, triangle must vanish -----
+template <typename T>
+static void syrk_executor_correctness() {
+  BLAS_Fixture f;
+  SYRK_Executor<T> syrk_exec;
+  GEMM_Executor<T> gemm_exec;
+  const int n = 213, k = 74;
+  for (bool lower : {false, true})
+    for (bool trans : {false, true})
+      for (auto &opts : SYRK_Options::enumerate()) {
+        TestMatrix<T> C(n, n), A(trans ? k : n, trans ? n : k);
+        {
+          GEMM_Inputs<T> in(f.handle, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, trans ? gpu::BLAS_OP_N : gpu::BLAS_OP_T, A, A, C, T(1), T(0));
+          gemm_exec.execute(in, GEMM_Options(), Workspace(), f.s);
+        }
+        {
+          SYRK_Inputs<T> in(f.handle, lower ? gpu::BLAS_FILL_MODE_LOWER : gpu::BLAS_FILL_MODE_UPPER, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, A,
+                            C, T(-1), T(1));
+          ManagedWorkspace space(syrk_exec.calculate_workspace(in, opts));
+          syrk_exec.execute(in, opts, space, f.s);
+        }
+        f.s.synchronize();
+        C.download();
+        bool other_nonzero = false;
+        for (int c = 0; c < n; c++)
+          for (int r = 0; r < n; r++) {
+            T &v = C.host[(size_t)c * C.ld + r];
+            if (lower ? r < c : r > c) {  // the triangle SYRK does not own keeps the GEMM result (beta = 1)
+              other_nonzero = other_nonzero || std::abs(v) > TestMatrix<T>::eps();
+              v = 0;
+            }
+          }
+        EXPECT_TRUE(other_nonzero);
+        EXPECT_TRUE(C.is_zero());
+      }
+}
+TEST(SYRK_Executor_Test, SYRK_Correctness_Double) { syrk_executor_correctness<double>(); }
+TEST(SYRK_Executor_Test, SYRK_Correctness_Single) { syrk_executor_correctness<float>(); }
+
+TEST(Facade_Test, Syrk_And_Trsm_Planners) {
+  class rtat r;
+  auto &sp = r.syrk_planner<double>();
+  auto &tp = r.trsm_planner<float>();
+  EXPECT_EQ(std::string(sp.create_plan(SYRK_Key(gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N, 64, 32))), "FF");
+  EXPECT_EQ(std::string(tp.create_plan(TRSM_Key(gpu::BLAS_SIDE_LEFT, gpu::BLAS_FILL_MODE_UPPER, gpu::BLAS_OP_T, gpu::BLAS_DIAG_UNIT, 64, 32))), "FF");
+}
+
 // ---- tests/matrixop_test.cpp -----------------------------------------------------------------------
 TEST(MatrixOp_Test, MoveTest) {
   BLAS_Fixture f;

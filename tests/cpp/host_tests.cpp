@@ -230,6 +230,109 @@ TEST(MatrixOp_Test, Shape_Checks_Are_Fatal) {
   ASSERT_EQ(mv.scratch_space_req(), 0u);
 }
 
+// ---- SYRK / TRSM host pieces (reference src/methods/syrk.{h,cpp}, trsm.{h,cpp}, json_encoding.h:110-223) ----------
+TEST(SYRK_TRSM_Test, Key_Text_Ordering_And_Json) {
+  SYRK_Key sk(gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_T, 213, 74);
+  ASSERT_EQ(std::string(sk), std::string("Lower,T,213,74"));
+  ASSERT_TRUE(SYRK_Key(gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N, 9, 9) < SYRK_Key(gpu::BLAS_FILL_MODE_UPPER, gpu::BLAS_OP_N, 1, 1));
+  ASSERT_TRUE(SYRK_Key(gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N, 1024, 8) < SYRK_Key(gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N, 128, 8));  // text order
+  ASSERT_EQ(to_json(sk).dump(), std::string("{\"k\":74,\"n\":213,\"trans\":\"T\",\"uplo\":\"Lower\"}"));
+  ASSERT_EQ(std::string(from_json<SYRK_Key>(to_json(sk))), std::string(sk));
+  ASSERT_EQ(sk.flopcount(), 213.0 * 214.0 * 74.0);
+
+  TRSM_Key tk(gpu::BLAS_SIDE_LEFT, gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N, gpu::BLAS_DIAG_NON_UNIT, 435, 527);
+  ASSERT_EQ(std::string(tk), std::string("Left,Lower,N,Non-Unit,435,527"));
+  TRSM_Key tk2(gpu::BLAS_SIDE_RIGHT, gpu::BLAS_FILL_MODE_UPPER, gpu::BLAS_OP_T, gpu::BLAS_DIAG_UNIT, 3, 5);
+  ASSERT_EQ(std::string(tk2), std::string("Right,Upper,T,Unit,3,5"));
+  ASSERT_TRUE(tk < tk2);
+  ASSERT_EQ(to_json(tk2).dump(), std::string("{\"diag\":\"Unit\",\"m\":3,\"n\":5,\"side\":\"Right\",\"trans\":\"T\",\"uplo\":\"Upper\"}"));
+  ASSERT_EQ(std::string(from_json<TRSM_Key>(to_json(tk))), std::string(tk));
+  ASSERT_EQ(tk.flopcount(), 435.0 * 435.0 * 527.0);
+  ASSERT_EQ(tk2.flopcount(), 5.0 * 5.0 * 3.0);
+}
+
+template <typename Opts>
+static void check_bool_plan_space(const char *json_first, const char *json_second) {
+  auto all = Opts::enumerate();
+  ASSERT_EQ(all.size(), 4u);
+  const char *names[4] = {"FF", "FT", "TF", "TT"};
+  for (int i = 0; i < 4; i++) {
+    ASSERT_EQ(std::string(all[i]), std::string(names[i]));
+    Opts parsed;
+    std::istringstream in(names[i]);
+    ASSERT_TRUE(bool(in >> parsed));
+    ASSERT_EQ(std::string(parsed), std::string(names[i]));  // the reference's >> always yields "TT" (syrk.cpp:64-65)
+    Json j = to_json(all[i]);
+    ASSERT_EQ(j[json_first].template get<std::string>(), std::string(1, names[i][0]));
+    ASSERT_EQ(j[json_second].template get<std::string>(), std::string(1, names[i][1]));
+    ASSERT_EQ(std::string(from_json<Opts>(j)), std::string(names[i]));
+  }
+  ASSERT_EQ(std::string(Opts::default_opts()), std::string("FF"));
+  Opts bad;
+  std::istringstream three("FFF");
+  ASSERT_TRUE(!(three >> bad));
+}
+TEST(SYRK_TRSM_Test, Options_Enumeration_Text_And_Json) {
+  check_bool_plan_space<SYRK_Options>("transA", "transC");
+  check_bool_plan_space<TRSM_Options>("swap_side", "transA");
+}
+
+TEST(SYRK_TRSM_Test, Workspace_Accounting) {
+  // SYRK: [transpose_C] n*n + [transpose_A] n*k elements (syrk.cpp:72-104 through matrixop.h:172-185)
+  for (bool trans : {false, true}) {
+    const size_t n = 213, k = 74, ar = trans ? k : n, ac = trans ? n : k;
+    Matrix<double> A(Workspace((double *)nullptr, ar * ac), ar, ac, ar), C(Workspace((double *)nullptr, n * n), n, n, n);
+    SYRK_Inputs<double> in(nullptr, gpu::BLAS_FILL_MODE_UPPER, trans ? gpu::BLAS_OP_T : gpu::BLAS_OP_N, A, C, 1.0, 0.0);
+    ASSERT_EQ(in.n(), n);
+    ASSERT_EQ(in.k(), k);
+    for (auto o : SYRK_Options::enumerate()) {
+      auto op = o.form_operation(in);
+      ASSERT_EQ(op->workspace_req_bytes(), sizeof(double) * ((o.transpose_A ? n * k : 0) + (o.transpose_C ? n * n : 0)));
+      ASSERT_EQ(op->output_space_req(), 0u);
+      ASSERT_EQ(op->dims().m, n);
+    }
+  }
+  // TRSM: [swap_side] n*m + [transpose_A] na*na elements (trsm.cpp:72-113)
+  for (bool left : {false, true}) {
+    const size_t m = 435, n = 527, na = left ? m : n;
+    Matrix<float> A(Workspace((float *)nullptr, na * na), na, na, na), B(Workspace((float *)nullptr, m * n), m, n, m);
+    TRSM_Inputs<float> in(nullptr, left ? gpu::BLAS_SIDE_LEFT : gpu::BLAS_SIDE_RIGHT, gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_N,
+                          gpu::BLAS_DIAG_UNIT, A, B, 1.f);
+    for (auto o : TRSM_Options::enumerate()) {
+      auto op = o.form_operation(in);
+      ASSERT_EQ(op->workspace_req_bytes(), sizeof(float) * ((o.swap_side ? m * n : 0) + (o.transpose_A ? na * na : 0)));
+      ASSERT_EQ(op->dims().m, m);
+      ASSERT_EQ(op->dims().n, n);
+    }
+  }
+  // shape checks are fatal, like the reference's bare `throw;`
+  auto mk = [](size_t r, size_t c) {
+    return std::unique_ptr<MatrixOp<double>>(std::make_unique<NoOp<double>>(Matrix<double>(Workspace((double *)nullptr, r * c), r, c, r)));
+  };
+  ASSERT_DEATH(MatrixSyrk<double>(mk(5, 3), mk(4, 4), true, false, 1.0, 0.0));          // n mismatch
+  ASSERT_DEATH(MatrixSyrk<double>(mk(4, 3), mk(4, 5), true, false, 1.0, 0.0));          // C not square
+  ASSERT_DEATH(MatrixTrs<double>(mk(4, 4), mk(5, 3), true, true, false, false, 1.0));   // left: mB != mA
+  ASSERT_DEATH(MatrixTrs<double>(mk(4, 5), mk(4, 3), true, true, false, false, 1.0));   // A not square
+  MatrixSyrkAlloc<double> sa(mk(3, 7), false, true, 1.0, 4);
+  ASSERT_EQ(sa.dims().m, 7u); ASSERT_EQ(sa.dims().ld, 8u); ASSERT_EQ(sa.output_space_req(), 56u);
+}
+
+TEST(SYRK_TRSM_Test, Facade_Planners_And_Plan_Cache) {
+  ::rtat::rtat r;
+  auto &sp = r.syrk_planner<double>();
+  ASSERT_EQ(&sp, &r.syrk_planner<double>());
+  auto &tp = r.trsm_planner<float>();
+  ASSERT_NE((void *)&tp, (void *)&r.trsm_planner<double>());
+  Json cache = Json::parse("[{\"key\": {\"uplo\":\"Upper\",\"trans\":\"N\",\"n\":4096,\"k\":512}, \"option\": {\"transA\":\"T\",\"transC\":\"F\"}}]");
+  ASSERT_EQ(sp.load_plans(cache), 1u);
+  ASSERT_EQ(std::string(sp.create_plan(SYRK_Key(gpu::BLAS_FILL_MODE_UPPER, gpu::BLAS_OP_N, 4096, 512))), std::string("TF"));
+  ASSERT_EQ(sp.save_plans(), cache);
+  Json tcache = Json::parse("[{\"key\": {\"side\":\"Right\",\"uplo\":\"Lower\",\"trans\":\"T\",\"diag\":\"Unit\",\"m\":100,\"n\":200}, \"option\": {\"swap_side\":\"T\",\"transA\":\"T\"}}]");
+  ASSERT_EQ(tp.load_plans(tcache), 1u);
+  ASSERT_EQ(std::string(tp.create_plan(TRSM_Key(gpu::BLAS_SIDE_RIGHT, gpu::BLAS_FILL_MODE_LOWER, gpu::BLAS_OP_T, gpu::BLAS_DIAG_UNIT, 100, 200))),
+            std::string("TT"));
+}
+
 TEST(Facade_Test, Lazy_Planners) {
   ::rtat::rtat r;
   auto &d1 = r.gemm_planner<double>();

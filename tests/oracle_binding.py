@@ -23,10 +23,22 @@ class Oracle:
             getattr(lib, f"oracle_{s}geam").restype = None
             getattr(lib, f"oracle_{s}gemm_plan").argtypes = [C.c_char_p, i, i, i, i, i, ct, vp, i, vp, i, ct, vp, i, vp, sz]
             getattr(lib, f"oracle_{s}gemm_plan").restype = i
+            getattr(lib, f"oracle_{s}syrk").argtypes = [i, i, i, i, ct, vp, i, ct, vp, i]
+            getattr(lib, f"oracle_{s}syrk").restype = None
+            getattr(lib, f"oracle_{s}trsm").argtypes = [i, i, i, i, i, i, ct, vp, i, vp, i]
+            getattr(lib, f"oracle_{s}trsm").restype = None
+            getattr(lib, f"oracle_{s}syrk_plan").argtypes = [C.c_char_p, i, i, i, i, ct, vp, i, ct, vp, i, vp, sz]
+            getattr(lib, f"oracle_{s}syrk_plan").restype = i
+            getattr(lib, f"oracle_{s}trsm_plan").argtypes = [C.c_char_p, i, i, i, i, i, i, ct, vp, i, vp, i, vp, sz]
+            getattr(lib, f"oracle_{s}trsm_plan").restype = i
             getattr(lib, f"oracle_fill_uniform_{s}").argtypes = [vp, sz, u64, ct, ct]
             getattr(lib, f"oracle_fill_uniform_{s}").restype = None
         lib.oracle_gemm_plan_workspace.argtypes = [C.c_char_p, i, i, i, i, i, sz]
         lib.oracle_gemm_plan_workspace.restype = sz
+        lib.oracle_syrk_plan_workspace.argtypes = [C.c_char_p, i, i, i, sz]
+        lib.oracle_syrk_plan_workspace.restype = sz
+        lib.oracle_trsm_plan_workspace.argtypes = [C.c_char_p, i, i, i, sz]
+        lib.oracle_trsm_plan_workspace.restype = sz
 
     @staticmethod
     def _s(dtype):
@@ -68,6 +80,36 @@ class Oracle:
         return rc, ws
 
 
+    # ---- SYRK / TRSM (flags are 0/1: lower, trans, left, unit) ------------------------------------
+    def syrk(self, lower, trans, n, k, alpha, A, lda, beta, Cm, ldc):
+        getattr(self.lib, f"oracle_{self._s(Cm.dtype)}syrk")(lower, trans, n, k, alpha, A.ctypes.data, lda, beta, Cm.ctypes.data, ldc)
+        return Cm
+
+    def trsm(self, left, lower, trans, unit, m, n, alpha, A, lda, B, ldb):
+        getattr(self.lib, f"oracle_{self._s(B.dtype)}trsm")(left, lower, trans, unit, m, n, alpha, A.ctypes.data, lda, B.ctypes.data, ldb)
+        return B
+
+    def syrk_plan_workspace(self, plan, trans, n, k, elem):
+        return self.lib.oracle_syrk_plan_workspace(plan.encode(), trans, n, k, elem)
+
+    def trsm_plan_workspace(self, plan, left, m, n, elem):
+        return self.lib.oracle_trsm_plan_workspace(plan.encode(), left, m, n, elem)
+
+    def syrk_plan(self, plan, lower, trans, n, k, alpha, A, lda, beta, Cm, ldc):
+        need = self.syrk_plan_workspace(plan, trans, n, k, Cm.dtype.itemsize)
+        ws = np.full(need // Cm.dtype.itemsize + 1, np.nan, dtype=Cm.dtype)
+        rc = getattr(self.lib, f"oracle_{self._s(Cm.dtype)}syrk_plan")(plan.encode(), lower, trans, n, k, alpha, A.ctypes.data, lda, beta,
+                                                                     Cm.ctypes.data, ldc, ws.ctypes.data, need)
+        return rc, ws
+
+    def trsm_plan(self, plan, left, lower, trans, unit, m, n, alpha, A, lda, B, ldb):
+        need = self.trsm_plan_workspace(plan, left, m, n, B.dtype.itemsize)
+        ws = np.full(need // B.dtype.itemsize + 1, np.nan, dtype=B.dtype)
+        rc = getattr(self.lib, f"oracle_{self._s(B.dtype)}trsm_plan")(plan.encode(), left, lower, trans, unit, m, n, alpha, A.ctypes.data, lda,
+                                                                    B.ctypes.data, ldb, ws.ctypes.data, need)
+        return rc, ws
+
+
 _cached = None
 
 
@@ -92,5 +134,6 @@ def view(buf, rows, cols, ld):
     return np.lib.stride_tricks.as_strided(buf, shape=(rows, cols), strides=(buf.itemsize, ld * buf.itemsize))
 
 
+BOOL_PLANS = ["FF", "FT", "TF", "TT"]  # SYRK_Options / TRSM_Options
 GEMM_PLANS = [a + b + c for a in "NT" for b in "NT" for c in "NT"]
 GEMM_PAD_PLANS = [a + b + c + d + e + f for a in "NT" for b in "NT" for c in "NT" for d in "NP" for e in "NP" for f in "NP"]

@@ -85,3 +85,10 @@ for m, n in [(1024, 1024), (4096, 4096), (8192, 8192)]:
 trsm(torch.float64, 8192, 8192, 0, 0, 1)
 trsm(torch.float64, 8192, 1024, 1, 0, 0)
 trsm(torch.float32, 8192, 8192, 1, 1, 0)
+for base in (64, 256):
+    h.set_option("trsm.base", base)
+    print(f"-- trsm.base = {base}")
+    trsm(torch.float64, 1024, 1024, 1, 1, 0)
+    trsm(torch.float64, 8192, 8192, 1, 1, 0)
+    trsm(torch.float64, 8192, 8192, 0, 0, 1)
+h.set_option("trsm.base", 0)

@@ -91,6 +91,7 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   cudaStreamSynchronize(h->stream);
   if (h->arena) cudaFree(h->arena);
   if (h->staging) cudaFree(h->staging);
+  if (h->trsm_inv) cudaFree(h->trsm_inv);
   if (h->sk_flags) cudaFree(h->sk_flags);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -309,6 +310,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   if (need > h->staging_bytes) {
     cudaStreamSynchronize(h->stream);
     if (h->staging) cudaFree(h->staging);
+  if (h->trsm_inv) cudaFree(h->trsm_inv);
     h->staging = nullptr;
     h->staging_bytes = 0;
     if (cudaMalloc(&h->staging, need) != cudaSuccess) {

@@ -15,6 +15,9 @@ struct rtat_b200_context {
   // library-owned device arena: stream-K partial tiles, pre-split operands, host-entry staging
   void *arena = nullptr;
   size_t arena_bytes = 0;
+  // TRSM: inverted 32 x 32 diagonal blocks of the current call (separate from the arena, which the GEMM updates use)
+  void *trsm_inv = nullptr;
+  size_t trsm_inv_bytes = 0;
   // tuning knobs (rtat_b200_set_option)
   std::map<std::string, int> options;
   // introspection

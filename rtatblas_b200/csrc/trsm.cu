@@ -1,97 +1,207 @@
 // TRSM:  solve  op(A) X = alpha B  (left)  or  X op(A) = alpha B  (right)  in place of B   (replaces cublasDtrsm /
 // cublasStrsm behind MatrixTrs / MatrixTrsAlloc, reference src/matrix_ops/matrixop.h:78-109, :442-534).
 //
-// Recursive blocked substitution: the triangular dimension is halved (at multiples of NB) until a block fits the
-// base kernel; between the two halves one GEMM folds the solved half into the other half's right-hand side,
+// Recursive blocked solve: the triangular dimension is halved (at multiples of 128) until a block fits the panel
+// kernel; between the two halves one GEMM folds the solved half into the other half's right-hand side,
 //     left,  op(A) lower:  X1 = A11 \ (alpha B1);  B2 = alpha B2 - A21 X1;  X2 = A22 \ B2
-// so for m >> NB practically all flops run in the DMMA / tcgen05 GEMM kernels on large k (the recursion hands the
-// GEMMs k = m/2, m/4, ... instead of the k = NB panels of a left-looking sweep).  The base kernel keeps one
-// right-hand-side vector per thread in NB registers and the NB x NB triangle in shared memory (every lane reads
-// the same element: a broadcast), and uses true divisions by the diagonal — no inverted blocks, so the result is
-// a plain substitution's, backward stable like the reference BLAS loop.  Only the `uplo` triangle of A is read
-// (not even its diagonal when diag == UNIT).
+// so for m >> 128 practically all flops run in the DMMA / tcgen05 GEMM kernels on large k (the recursion hands the
+// GEMMs k = m/2, m/4, ... instead of the k = 128 panels of a left-looking sweep).
+//
+// Diagonal blocks (<= 128 rows) are solved by trsm_panel_kernel: one CTA holds a 128 x 64 panel of right-hand sides
+// in shared memory and walks its four 32-row sub-blocks; per sub-block every thread owns a 2 x 4 patch of the
+// 32 x 64 result, so a step is two small dense products (fold the solved sub-blocks in, then apply the sub-block's
+// inverse) instead of a 32-step dependent chain per vector.  Only the 32 x 32 DIAGONAL sub-blocks are inverted (all
+// of them in one pre-pass launch per call, by substitution on the identity); everything off those sub-blocks is
+// plain substitution, which keeps the error growth that of a block substitution with well-conditioned 32 x 32 pivots.
+// Only the `uplo` triangle of A is read (not even its diagonal when diag == UNIT).
 #include "common.cuh"
 
 namespace rtat_b200 {
 
 namespace trsm {
 
-constexpr int NB = 32;        // base block: vector length held in registers
-constexpr int VECS = 128;     // right-hand-side vectors per CTA (one per thread)
+constexpr int NB = 32;        // inverted diagonal sub-block
+constexpr int BASE = 128;     // rows of one panel-kernel launch (default recursion cut-off, and its maximum)
+constexpr int V = 64;         // right-hand-side vectors per CTA
+constexpr int XS = V + 2;     // row stride of the panel in shared memory (even: 16 B vector loads stay aligned)
+constexpr int FS = NB + 2;    // row stride of the staged F rows
+constexpr int PANEL_THREADS = 256;
 
-// Solves F x = alpha b for VECS vectors per CTA, F = the nb x nb block at A (nb <= NB), normalised so that the
-// vectors are columns of B (LEFT) or rows of B (!LEFT, where F = op(A)^T).
-//   tr      F(i, j) = tr ? A(j, i) : A(i, j)
-//   lower_f F is lower triangular (forward substitution), else upper (backward)
-template <typename T, bool LEFT>
-__global__ void __launch_bounds__(VECS)
-trsm_base_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int nb, int nvec, T alpha, int tr, int lower_f, int unit) {
-  __shared__ T sF[NB * NB];               // sF[i * NB + j] = F(i, j); zero outside the triangle, 1 on padded diagonal
-  __shared__ T sB[LEFT ? VECS * (NB + 1) : 1];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += VECS) {
-    // fastest index follows A's contiguous dimension so the global reads coalesce
-    const int fast = idx % NB, slow = idx / NB;
-    const int i = tr ? slow : fast, j = tr ? fast : slow;  // F(i, j); A element (tr ? (j, i) : (i, j))
-    T v = T(0);
-    if (i < nb && j < nb) {
-      const bool in_tri = lower_f ? (i > j) : (i < j);
-      if (in_tri || (i == j && !unit)) v = tr ? A[(size_t)i * lda + j] : A[(size_t)j * lda + i];
-      else if (i == j) v = T(1);
-    } else if (i == j) {
-      v = T(1);
-    }
-    sF[i * NB + j] = v;
+// F is the triangular matrix normalised so that the right-hand-side vectors are columns of B (LEFT) or rows of B
+// (!LEFT, where F = op(A)^T):  F(i, j) = tr ? A(j, i) : A(i, j);  lower_f: F is lower triangular.
+
+// Pre-pass: inverse of every NB x NB diagonal block of F (identity-padded past na), by substitution on the columns
+// of the identity; block b is stored k-major: inv[(b * NB + k) * NB + i] = Finv_b(i, k).
+template <typename T>
+__global__ void __launch_bounds__(NB)
+trsm_diag_inverse_kernel(const T *__restrict__ A, int lda, int na, int tr, int lower_f, int unit, T *__restrict__ inv) {
+  __shared__ T sF[NB][NB + 1];
+  const int b = blockIdx.x, t = threadIdx.x, r0 = b * NB;
+  // element (i, j) of the block; lanes run along A's contiguous dimension.  All 32 loads first, then the stores.
+  T col[NB];
+#pragma unroll
+  for (int e = 0; e < NB; e++) {
+    const int i = tr ? e : t, j = tr ? t : e;
+    const int gi = r0 + i, gj = r0 + j;
+    col[e] = (i == j) ? T(1) : T(0);
+    if (gi < na && gj < na && ((lower_f ? i > j : i < j) || (i == j && !unit))) col[e] = tr ? A[(size_t)gi * lda + gj] : A[(size_t)gj * lda + gi];
   }
-  const int v0 = blockIdx.x * VECS;
+#pragma unroll
+  for (int e = 0; e < NB; e++) sF[tr ? e : t][tr ? t : e] = col[e];
+  __syncthreads();
+  __shared__ T sRec[NB];
+  sRec[t] = T(1) / sF[t][t];  // one division per diagonal entry, in parallel, instead of 32 in every thread's chain
+  __syncthreads();
   T x[NB];
-  if (LEFT) {
-    // stage the nb x VECS panel through shared memory: coalesced column segments in, one padded row per thread out
-    for (int idx = tid; idx < NB * VECS; idx += VECS) {
-      const int i = idx % NB, v = idx / NB;
-      sB[v * (NB + 1) + i] = (i < nb && v0 + v < nvec) ? B[(size_t)(v0 + v) * ldb + i] : T(0);
-    }
-    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NB; i++) x[i] = alpha * sB[tid * (NB + 1) + i];
-  } else {
-    __syncthreads();
-    const int r = v0 + tid;
-#pragma unroll
-    for (int i = 0; i < NB; i++) x[i] = (i < nb && r < nvec) ? alpha * B[(size_t)i * ldb + r] : T(0);
-  }
+  for (int i = 0; i < NB; i++) x[i] = (i == t) ? T(1) : T(0);
   if (lower_f) {
 #pragma unroll
     for (int i = 0; i < NB; i++) {
-      if (!unit) x[i] = x[i] / sF[i * NB + i];
+      x[i] *= sRec[i];
 #pragma unroll
-      for (int j = i + 1; j < NB; j++) x[j] -= sF[j * NB + i] * x[i];
+      for (int j = i + 1; j < NB; j++) x[j] -= sF[j][i] * x[i];
     }
   } else {
 #pragma unroll
     for (int i = NB - 1; i >= 0; i--) {
-      if (!unit) x[i] = x[i] / sF[i * NB + i];
+      x[i] *= sRec[i];
 #pragma unroll
-      for (int j = 0; j < i; j++) x[j] -= sF[j * NB + i] * x[i];
+      for (int j = 0; j < i; j++) x[j] -= sF[j][i] * x[i];
     }
   }
-  if (LEFT) {
+  T *out = inv + ((size_t)b * NB + t) * NB;
 #pragma unroll
-    for (int i = 0; i < NB; i++) sB[tid * (NB + 1) + i] = x[i];
+  for (int i = 0; i < NB; i++) out[i] = x[i];
+}
+
+// 4- or 8-byte asynchronous copy global -> shared; valid == false writes zeros without touching the source
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *dst_smem, const T *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? (int)sizeof(T) : 0;
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+constexpr int F_ROWS = NB * (0 + 1 + 2 + 3);  // staged rows of F over the four steps: 0 + 32 + 64 + 96
+
+// Solves F x = alpha b for V vectors per CTA, F = the s x s (s <= BASE) diagonal block at A whose NB x NB diagonal
+// sub-block inverses start at `inv`.  Everything the CTA needs — the panel, the strictly triangular part of F in
+// step order, the four inverses — is fetched with one burst of cp.async at entry, so global latency is paid once.
+template <typename T, bool LEFT>
+__global__ void __launch_bounds__(PANEL_THREADS)
+trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nvec, T alpha, int tr, int lower_f,
+                  const T *__restrict__ inv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sX = reinterpret_cast<T *>(smem_raw);   // [BASE][XS]: the panel, row = index along the triangular dimension
+  T *sF = sX + BASE * XS;                    // [F_ROWS][FS]: step t's rows at NB * t (t - 1) / 2: sF[kk][i] = F(r0 + i, k0 + kk)
+  T *sD = sF + F_ROWS * FS;                  // [nsub][NB][FS]: sD[sb][k][i] = Finv_sb(i, k)
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * V;
+  const int nsub = (s + NB - 1) / NB, rows = nsub * NB;
+
+  // ---- one burst of asynchronous copies ----
+  if (LEFT) {  // r fastest: columns of B are contiguous
+    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
+      const int r = idx % rows, v = idx / rows;
+      const bool ok = r < s && v0 + v < nvec;
+      cp_async_elem(sX + r * XS + v, ok ? B + (size_t)(v0 + v) * ldb + r : B, ok);
+    }
+  } else {     // v fastest: rows of B run along its contiguous dimension
+    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
+      const int v = idx % V, r = idx / V;
+      const bool ok = r < s && v0 + v < nvec;
+      cp_async_elem(sX + r * XS + v, ok ? B + (size_t)r * ldb + v0 + v : B, ok);
+    }
+  }
+  for (int step = 1; step < nsub; step++) {
+    const int sb = lower_f ? step : nsub - 1 - step, r0 = sb * NB;
+    const int k0 = lower_f ? 0 : r0 + NB, nk = step * NB;  // the rows solved before this step
+    T *dst = sF + (NB * step * (step - 1) / 2) * FS;
+    for (int idx = tid; idx < nk * NB; idx += PANEL_THREADS) {
+      const int i = tr ? idx / nk : idx % NB, kk = tr ? idx % nk : idx / NB;  // fastest index = A's contiguous one
+      const int gi = r0 + i, gk = k0 + kk;
+      const bool ok = gi < s && gk < s;
+      cp_async_elem(dst + kk * FS + i, ok ? (tr ? A + (size_t)gi * lda + gk : A + (size_t)gk * lda + gi) : A, ok);
+    }
+  }
+  for (int idx = tid; idx < nsub * NB * NB; idx += PANEL_THREADS)
+    cp_async_elem(sD + (idx / NB) * FS + idx % NB, inv + idx, true);
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+
+  // thread -> 2 rows x 4 vectors of the 32 x 64 sub-block result
+  const int warp = tid / 32, lane = tid % 32;
+  const int row = 16 * (warp / 4) + 2 * (lane / 4);   // 0..30, even
+  const int vec = 16 * (warp % 4) + 4 * (lane % 4);   // 0..60, multiple of 4
+
+  for (int step = 0; step < nsub; step++) {
+    const int sb = lower_f ? step : nsub - 1 - step, r0 = sb * NB;
+    const int k0 = lower_f ? 0 : r0 + NB, nk = step * NB;
+    const T *F = sF + (NB * step * (step - 1) / 2) * FS;
+    const T *D = sD + sb * NB * FS;
+    // R = alpha b_sb - F[sb, solved] X[solved]   (alpha was folded into the solved X already)
+    T acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[a][c] = alpha * sX[(r0 + row + a) * XS + vec + c];
+#pragma unroll 8
+    for (int kk = 0; kk < nk; kk++) {
+      const T f0 = F[kk * FS + row], f1 = F[kk * FS + row + 1];
+      const T *xr = sX + (k0 + kk) * XS + vec;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        acc[0][c] -= f0 * xr[c];
+        acc[1][c] -= f1 * xr[c];
+      }
+    }
+    // only their owner reads the b_sb entries -> publish R in their place
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
     __syncthreads();
-    for (int idx = tid; idx < NB * VECS; idx += VECS) {
-      const int i = idx % NB, v = idx / NB;
-      if (i < nb && v0 + v < nvec) B[(size_t)(v0 + v) * ldb + i] = sB[v * (NB + 1) + i];
+    // X_sb = Finv_sb R
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[a][c] = T(0);
+#pragma unroll 8
+    for (int kk = 0; kk < NB; kk++) {
+      const T f0 = D[kk * FS + row], f1 = D[kk * FS + row + 1];
+      const T *xr = sX + (r0 + kk) * XS + vec;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        acc[0][c] += f0 * xr[c];
+        acc[1][c] += f1 * xr[c];
+      }
+    }
+    __syncthreads();  // all reads of R done
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
+    __syncthreads();  // X_sb visible to the next step
+  }
+
+  // ---- panel out ----
+  if (LEFT) {
+    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
+      const int r = idx % rows, v = idx / rows;
+      if (r < s && v0 + v < nvec) B[(size_t)(v0 + v) * ldb + r] = sX[r * XS + v];
     }
   } else {
-    const int r = v0 + tid;
-    if (r < nvec) {
-#pragma unroll
-      for (int i = 0; i < NB; i++)
-        if (i < nb) B[(size_t)i * ldb + r] = x[i];
+    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
+      const int v = idx % V, r = idx / V;
+      if (r < s && v0 + v < nvec) B[(size_t)r * ldb + v0 + v] = sX[r * XS + v];
     }
   }
 }
+
+template <typename T>
+constexpr size_t panel_smem_bytes() { return sizeof(T) * (size_t(BASE) * XS + size_t(F_ROWS) * FS + size_t(BASE) * FS); }
 
 template <typename T>
 struct Problem {
@@ -103,29 +213,36 @@ struct Problem {
   T *B;
   int ldb;
   int (*gemm)(rtat_b200_context *, int, int, int, int, int, T, const T *, int, const T *, int, T, T *, int);
+  int base;       // diagonal blocks up to this size are solved by one trsm_panel_kernel launch
+  const T *inv;   // inverted NB x NB diagonal blocks of the whole triangle
+  bool tr, lower_f;
 };
 
-template <typename T>
-static int base(const Problem<T> &p, int o, int s, T alpha) {
-  const T *Ablk = p.A + (size_t)o * p.lda + o;
-  const bool tr = p.left ? p.trans : !p.trans;
-  const bool lower_f = tr ? !p.lower : p.lower;
-  if (p.left) {
-    const int grid = (p.n + VECS - 1) / VECS;
-    trsm_base_kernel<T, true><<<grid, VECS, 0, p.h->stream>>>(Ablk, p.lda, p.B + o, p.ldb, s, p.n, alpha, tr, lower_f, p.unit);
-  } else {
-    const int grid = (p.m + VECS - 1) / VECS;
-    trsm_base_kernel<T, false><<<grid, VECS, 0, p.h->stream>>>(Ablk, p.lda, p.B + (size_t)o * p.ldb, p.ldb, s, p.m, alpha, tr, lower_f, p.unit);
+template <typename T, bool LEFT>
+static int launch_panel(const Problem<T> &p, int o, int s, T alpha) {
+  auto kern = trsm_panel_kernel<T, LEFT>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_bytes<T>()) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_INTERNAL_ERROR;
+    }
+    configured = true;
   }
-  return check_launch(p.h, "trsm_base_nb32");
+  const int nvec = LEFT ? p.n : p.m;
+  const T *Ablk = p.A + (size_t)o * p.lda + o;
+  T *Bblk = LEFT ? p.B + o : p.B + (size_t)o * p.ldb;
+  kern<<<(nvec + V - 1) / V, PANEL_THREADS, panel_smem_bytes<T>(), p.h->stream>>>(Ablk, p.lda, Bblk, p.ldb, s, nvec, alpha, p.tr, p.lower_f,
+                                                                                   p.inv + (size_t)(o / NB) * NB * NB);
+  return check_launch(p.h, "trsm_panel_128x64");
 }
 
 // solves the part of the system that lives on [o, o + s) of the triangular dimension
 template <typename T>
 static int solve(const Problem<T> &p, int o, int s, T alpha) {
-  if (s <= NB) return base(p, o, s, alpha);
-  const int blocks = (s + NB - 1) / NB;
-  const int s1 = (blocks + 1) / 2 * NB, s2 = s - s1, o1 = o, o2 = o + s1;
+  if (s <= p.base) return p.left ? launch_panel<T, true>(p, o, s, alpha) : launch_panel<T, false>(p, o, s, alpha);
+  const int blocks = (s + p.base - 1) / p.base;
+  const int s1 = (blocks + 1) / 2 * p.base, s2 = s - s1, o1 = o, o2 = o + s1;
   const bool lower_eff = p.lower != p.trans;           // shape of op(A)
   const bool first_first = p.left ? lower_eff : !lower_eff;
   // the off-diagonal block of A that couples the halves lies below the diagonal for a lower A, above for an upper A
@@ -160,8 +277,34 @@ static int run(rtat_b200_context *h, int side, int uplo, int trans, int diag, in
     return RTAT_B200_STATUS_SUCCESS;
   }
   Problem<T> p{h, side == RTAT_B200_SIDE_LEFT, uplo == RTAT_B200_FILL_LOWER, trans != RTAT_B200_OP_N, diag == RTAT_B200_DIAG_UNIT,
-               m, n, A, lda, B, ldb, gemm};
-  int st = solve(p, 0, p.left ? m : n, alpha);
+               m, n, A, lda, B, ldb, gemm, 0, nullptr, false, false};
+  // trsm.base: recursion cut-off (a multiple of NB, at most BASE); smaller = more of the work in the GEMM kernels
+  p.base = opt(h, "trsm.base", 0);
+  if (p.base <= 0 || p.base > BASE) p.base = BASE;
+  p.base = (p.base + NB - 1) / NB * NB;
+  p.tr = p.left ? p.trans : !p.trans;
+  p.lower_f = p.tr ? !p.lower : p.lower;
+  const int na = p.left ? m : n, nblk = (na + NB - 1) / NB;
+  const size_t need = sizeof(T) * (size_t)nblk * NB * NB;
+  if (need > h->trsm_inv_bytes) {
+    if (h->trsm_inv) {
+      cudaStreamSynchronize(h->stream);  // an earlier call may still be reading it
+      cudaFree(h->trsm_inv);
+      h->trsm_inv = nullptr;
+      h->trsm_inv_bytes = 0;
+    }
+    const size_t want = (need + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    if (cudaMalloc(&h->trsm_inv, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_ALLOC_FAILED;
+    }
+    h->trsm_inv_bytes = want;
+  }
+  p.inv = static_cast<const T *>(h->trsm_inv);
+  trsm_diag_inverse_kernel<T><<<nblk, NB, 0, h->stream>>>(A, lda, na, p.tr, p.lower_f, p.unit, static_cast<T *>(h->trsm_inv));
+  int st = check_launch(h, "trsm_diag_inverse_32");
+  if (st) return st;
+  st = solve(p, 0, na, alpha);
   if (!st) h->last_kernel = name;
   return st;
 }
@@ -170,12 +313,12 @@ static int run(rtat_b200_context *h, int side, int uplo, int trans, int diag, in
 
 int dtrsm(rtat_b200_context *h, int side, int uplo, int trans, int diag, int m, int n, double alpha, const double *A, int lda, double *B,
           int ldb) {
-  return trsm::run<double>(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, dgemm, "dtrsm_recursive_nb32_dmma");
+  return trsm::run<double>(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, dgemm, "dtrsm_recursive_dmma");
 }
 
 int strsm(rtat_b200_context *h, int side, int uplo, int trans, int diag, int m, int n, float alpha, const float *A, int lda, float *B,
           int ldb) {
-  return trsm::run<float>(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, sgemm, "strsm_recursive_nb32_3xtf32");
+  return trsm::run<float>(h, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, sgemm, "strsm_recursive_3xtf32");
 }
 
 }  // namespace rtat_b200

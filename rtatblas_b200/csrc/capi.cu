@@ -310,7 +310,6 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   if (need > h->staging_bytes) {
     cudaStreamSynchronize(h->stream);
     if (h->staging) cudaFree(h->staging);
-  if (h->trsm_inv) cudaFree(h->trsm_inv);
     h->staging = nullptr;
     h->staging_bytes = 0;
     if (cudaMalloc(&h->staging, need) != cudaSuccess) {

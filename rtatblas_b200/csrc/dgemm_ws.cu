@@ -430,7 +430,9 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
 
-    // epilogue: lane (q,g) of block (i,j) holds C[row(i,g)][col(j,2q+e)]
+    // epilogue: lane (q,g) of block (i,j) holds C[row(i,g)][col(j,2q+e)].  With beta != 0 the MI loads of a column
+    // are issued together before the first store: a load-modify-store loop would serialise on one DRAM latency per
+    // element (C aliases itself, so the compiler cannot hoist the loads).
 #pragma unroll
     for (int j = 0; j < NI; j++) {
 #pragma unroll
@@ -438,14 +440,25 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         int col = n0 + wn0 + phys_index<KCB>(j, 2 * q + e);
         if (col >= p.n) continue;
         double *ccol = p.C + (size_t)col * p.ldc;
+        bool ok[MI];
+        double old[MI];
 #pragma unroll
         for (int i = 0; i < MI; i++) {
           int row = m0 + wm0 + phys_index<KCA>(i, g);
-          if (TRI && (p.tri == 1 ? row < col : row > col)) continue;
-          if (row < p.m) {
+          ok[i] = row < p.m && !(TRI && (p.tri == 1 ? row < col : row > col));
+          old[i] = 0.0;
+        }
+        if (beta != 0.0) {
+#pragma unroll
+          for (int i = 0; i < MI; i++)
+            if (ok[i]) old[i] = ccol[m0 + wm0 + phys_index<KCA>(i, g)];
+        }
+#pragma unroll
+        for (int i = 0; i < MI; i++) {
+          if (ok[i]) {
             double v = alpha * acc[i][j][e];
-            if (beta != 0.0) v += beta * ccol[row];
-            ccol[row] = v;
+            if (beta != 0.0) v += beta * old[i];
+            ccol[m0 + wm0 + phys_index<KCA>(i, g)] = v;
           }
         }
       }

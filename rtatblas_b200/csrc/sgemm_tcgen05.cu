@@ -368,14 +368,30 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
       const int row = m0 + quarter * 32 + lane;
       if (row < p.m) {
+        // 8 columns at a time: with beta != 0 the 8 loads go out together before the first store (a
+        // load-modify-store loop would pay one DRAM latency per element, C aliasing itself)
 #pragma unroll
-        for (int j = 0; j < BN; j++) {
-          const int col = n0 + j;
-          if (col < p.n && !(p.tri == 1 && row < col) && !(p.tri == 2 && row > col)) {
-            float *dst = p.C + (size_t)col * p.ldc + row;
-            float v = alpha * sum[j];
-            if (beta != 0.f) v += beta * *dst;
-            *dst = v;
+        for (int j0 = 0; j0 < BN; j0 += 8) {
+          float old[8];
+          bool ok[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int col = n0 + j0 + j;
+            ok[j] = col < p.n && !(p.tri == 1 && row < col) && !(p.tri == 2 && row > col);
+            old[j] = 0.f;
+          }
+          if (beta != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (ok[j]) old[j] = p.C[(size_t)(n0 + j0 + j) * p.ldc + row];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (ok[j]) {
+              float v = alpha * sum[j0 + j];
+              if (beta != 0.f) v += beta * old[j];
+              p.C[(size_t)(n0 + j0 + j) * p.ldc + row] = v;
+            }
           }
         }
       }

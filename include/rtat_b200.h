@@ -140,9 +140,11 @@ uint64_t rtat_b200_launch_count(rtat_b200_handle_t handle);
 
 /* ---- host-buffer entry points ---------------------------------------------------------------------
  * Same contract as dgemm/sgemm but A, B, C are HOST pointers (pinned or pageable).  Operands are
- * staged through the handle's device arena (grown on demand) as a pipeline over column blocks of
- * op(B) / C: H2D of block j+1, the GEMM of block j (on the handle's stream) and D2H of block j-1
- * overlap on separate streams; the call returns after C is valid on the host.  This is what a caller that
+ * staged through the handle's device arena (grown on demand) as a pipeline on three streams: large
+ * problems first stream A in K-panels against the leading column blocks of op(B) / C (so the math starts
+ * after the first panel instead of after all of A), then run whole-K column blocks — H2D of block j+1,
+ * the GEMM of block j (on the handle's stream) and D2H of block j-1 overlap; the call returns after C is
+ * valid on the host.  This is what a caller that
  * keeps its matrices in host memory sees, and what bench.py times as the end-to-end number. */
 int rtat_b200_dgemm_host(rtat_b200_handle_t handle, int transa, int transb, int m, int n, int k,
                          const double *alpha, const double *A, int lda, const double *B, int ldb,

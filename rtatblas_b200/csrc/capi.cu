@@ -335,42 +335,84 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
       if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return RTAT_B200_STATUS_ALLOC_FAILED;
   }
   cudaStream_t s = h->stream, sin = h->copy_in, sout = h->copy_out;
-  constexpr int MAX_BLOCKS = 8;
-  // column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128
+  constexpr int MAX_BLOCKS = 8, MAX_PANELS = 8;
+  // Column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128.
   int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
   nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
   const int blocks = (n + nb - 1) / nb;
-  cudaEvent_t *ev = h->host_events;  // [0] entry fence, [1] A landed, [2 + j] B_j landed, [10 + j] C_j computed
+  // Schedule.  Every column block needs all of A, so a plain column-block pipeline idles the GPU while A crosses
+  // PCIe.  Phase 1 therefore runs the first `lead` column blocks K-panel by K-panel: panel p of A and the matching
+  // pieces of those blocks are copied, then multiplied (beta, then 1) while panel p + 1 is in flight.  `lead` is
+  // chosen so that those blocks' math takes about as long as copying A plus their own share of B.  Phase 2 is the
+  // column-block pipeline for the rest (A is resident by then): copy B_j, multiply, copy C_j back.
+  int panels = 1, lead = 0;
+  if (blocks > 1 && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
+    panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
+    const double pcie = 50e9, rate = sizeof(T) == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
+    const double t_a = double(bytes_a) / pcie, t_b = double(sizeof(T)) * k * nb / pcie, t_mm = 2.0 * m * nb * double(k) / rate;
+    lead = t_mm > t_b ? int(t_a / (t_mm - t_b) + 0.5) : blocks;
+    if (lead < 1) lead = 1;
+    // host.panels / host.lead: overrides for experiments (0 = the choice above)
+    if (opt(h, "host.panels") > 0) panels = opt(h, "host.panels") < MAX_PANELS ? opt(h, "host.panels") : MAX_PANELS;
+    if (opt(h, "host.lead") > 0) lead = opt(h, "host.lead");
+    if (lead > blocks) lead = blocks;
+  }
+  const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
+  cudaEvent_t *ev = h->host_events;
+  int next_event = 1;  // [0] is the entry fence
+  auto landed = [&]() {  // everything queued on the H2D stream so far is visible to the math stream after this
+    cudaEvent_t e = ev[next_event++];
+    cudaEventRecord(e, sin);
+    cudaStreamWaitEvent(s, e, 0);
+  };
+  // stored element (row, col) of a column-major host/device pair -> 2-D copy of a rows x cols window
+  auto h2d_window = [&](T *dst, const T *src, int ld, size_t row0, size_t col0, size_t rows, size_t cols) {
+    const size_t off = col0 * ld + row0;
+    if (rows == (size_t)ld) return cudaMemcpyAsync(dst + off, src + off, sizeof(T) * rows * cols, cudaMemcpyHostToDevice, sin);
+    return cudaMemcpy2DAsync(dst + off, sizeof(T) * ld, src + off, sizeof(T) * ld, sizeof(T) * rows, cols, cudaMemcpyHostToDevice, sin);
+  };
+  auto d2h_block = [&](int j0, int cnt) {  // only the m x cnt window (ldc padding rows on the host are left untouched)
+    cudaEvent_t e = ev[next_event++];
+    cudaEventRecord(e, s);
+    cudaStreamWaitEvent(sout, e, 0);
+    return cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
+                                     cudaMemcpyDeviceToHost, sout), "D2H C");
+  };
   if (!cuda_ok(cudaEventRecord(ev[0], s), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
   cudaStreamWaitEvent(sin, ev[0], 0);
-  if (!cuda_ok(cudaMemcpyAsync(dA, A, sizeof(T) * lda * cols_a, cudaMemcpyHostToDevice, sin), "H2D A")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-  cudaEventRecord(ev[1], sin);
-  cudaStreamWaitEvent(s, ev[1], 0);
-  for (int j = 0; j < blocks; j++) {
+
+  // ---- phase 1: K-panels of A against the first `lead` column blocks (panels == 1: all of A, no blocks) ----
+  for (int p = 0; p < panels; p++) {
+    const int p0 = p * kp, kc = p0 + kp > k ? k - p0 : kp;
+    if (kc <= 0) break;
+    // A is stored m x k (N) or k x m (T): the panel is a column block or a row block
+    cudaError_t e = transa == RTAT_B200_OP_N ? h2d_window(dA, A, lda, 0, p0, m, kc) : h2d_window(dA, A, lda, p0, 0, kc, m);
+    if (!cuda_ok(e, "H2D A")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    for (int j = 0; j < lead; j++) {
+      const int j0 = j * nb, cnt = (j0 + nb > n) ? n - j0 : nb;
+      // op(B) block j, K-panel p: B is stored k x n (N) or n x k (T)
+      e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, p0, j0, kc, cnt) : h2d_window(dB, B, ldb, j0, p0, cnt, kc);
+      if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+      if (p == 0 && *beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+      landed();
+      const T *Ap = transa == RTAT_B200_OP_N ? dA + (size_t)p0 * lda : dA + p0;
+      const T *Bjp = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb + p0 : dB + (size_t)p0 * ldb + j0;
+      st = gemm_fn(h, transa, transb, m, cnt, kc, *alpha, Ap, lda, Bjp, ldb, p == 0 ? *beta : T(1), dC + (size_t)j0 * ldc, ldc);
+      if (st) return st;
+      if (p0 + kc >= k && !d2h_block(j0, cnt)) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    }
+  }
+  // ---- phase 2: whole-K column blocks ----
+  for (int j = lead; j < blocks; j++) {
     const int j0 = j * nb, cnt = (j0 + nb > n) ? n - j0 : nb;
-    // ---- H2D: columns [j0, j0 + cnt) of op(B) (and of C when beta != 0)
-    cudaError_t e;
-    if (transb == RTAT_B200_OP_N)
-      e = cudaMemcpyAsync(dB + (size_t)j0 * ldb, B + (size_t)j0 * ldb, sizeof(T) * (size_t)ldb * cnt, cudaMemcpyHostToDevice, sin);
-    else  // B is stored n x k: the block is rows [j0, j0 + cnt) of every column
-      e = cudaMemcpy2DAsync(dB + j0, sizeof(T) * ldb, B + j0, sizeof(T) * ldb, sizeof(T) * cnt, k, cudaMemcpyHostToDevice, sin);
+    cudaError_t e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, 0, j0, k, cnt) : h2d_window(dB, B, ldb, j0, 0, cnt, k);
     if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    if (*beta != T(0) &&
-        !cuda_ok(cudaMemcpy2DAsync(dC + (size_t)j0 * ldc, sizeof(T) * ldc, C + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
-                                   cudaMemcpyHostToDevice, sin), "H2D C"))
-      return RTAT_B200_STATUS_EXECUTION_FAILED;
-    cudaEventRecord(ev[2 + j], sin);
-    // ---- math on the handle's stream
-    cudaStreamWaitEvent(s, ev[2 + j], 0);
+    if (*beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    landed();
     const T *Bj = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb : dB + j0;
     st = gemm_fn(h, transa, transb, m, cnt, k, *alpha, dA, lda, Bj, ldb, *beta, dC + (size_t)j0 * ldc, ldc);
     if (st) return st;
-    cudaEventRecord(ev[2 + MAX_BLOCKS + j], s);
-    // ---- D2H: only the m x cnt window (ldc padding rows on the host are left untouched)
-    cudaStreamWaitEvent(sout, ev[2 + MAX_BLOCKS + j], 0);
-    if (!cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
-                                   cudaMemcpyDeviceToHost, sout), "D2H C"))
-      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    if (!d2h_block(j0, cnt)) return RTAT_B200_STATUS_EXECUTION_FAILED;
   }
   if (!cuda_ok(cudaStreamSynchronize(sout), "synchronize") || !cuda_ok(cudaStreamSynchronize(s), "synchronize"))
     return RTAT_B200_STATUS_EXECUTION_FAILED;

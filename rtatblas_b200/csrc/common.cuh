@@ -30,7 +30,7 @@ struct rtat_b200_context {
   void *staging = nullptr;
   size_t staging_bytes = 0;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H side streams of the host entry points
-  cudaEvent_t host_events[2 + 2 * 8] = {};
+  cudaEvent_t host_events[96] = {};  // entry fence + one per staged piece + one per finished column block
 };
 
 namespace rtat_b200 {

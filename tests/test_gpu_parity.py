@@ -318,6 +318,35 @@ def test_gemm_host_entry(oracle, handle, dtype):
             assert np.array_equal(view(got, ldc, n, ldc)[m:], view(C0, ldc, n, ldc)[m:])  # host padding rows untouched
 
 
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_gemm_host_entry_k_panel_pipeline(handle, ta, tb):
+    """A of 32 MiB and k >= 2048 switch the host entry to its two-phase schedule (K-panels of A against the leading
+    column blocks, then whole-K column blocks): every op pair, beta != 0, padded leading dimensions.  Checked against
+    cuBLAS' product (torch, test-only use) within twice the stated bound, like the full-size configs."""
+    m, n, k, pad, alpha, beta = 2048, 600, 2051, 2, 0.75, -0.5
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    lda, ldb, ldc = ar + pad, br + pad, m + pad
+    g = torch.Generator().manual_seed(77)
+    hA = (torch.rand(lda * ac, dtype=torch.float64, generator=g) * 2 - 1).pin_memory()
+    hB = torch.rand(ldb * bc, dtype=torch.float64, generator=g) * 2 - 1
+    C0 = torch.rand(ldc * n, dtype=torch.float64, generator=g) * 2 - 1
+    hC = C0.clone()
+    launches = handle.launch_count()
+    handle.gemm(True, ta, tb, m, n, k, alpha, hA, lda, hB, ldb, beta, hC, ldc, host=True)
+    assert handle.launch_count() - launches > 3, "expected one GEMM per (column block, K-panel) of the leading blocks"
+    Am = hA.view(ac, lda).t()[:ar].cuda()
+    Bm = hB.view(bc, ldb).t()[:br].cuda()
+    opA, opB = (Am.t() if ta else Am), (Bm.t() if tb else Bm)
+    Cin = C0.view(n, ldc).t()[:m].cuda()
+    ref = alpha * (opA @ opB) + beta * Cin
+    bound = abs(alpha) * (opA.abs() @ opB.abs()) + abs(beta) * Cin.abs()
+    got = hC.view(n, ldc).t()
+    eps = np.finfo(np.float64).eps
+    assert bool(torch.all((got[:m].cuda() - ref).abs() <= 2 * 2 * k * eps * bound + 2 * eps * ref.abs()))
+    assert torch.equal(got[m:], C0.view(n, ldc).t()[m:])  # host padding rows untouched
+
+
 # ---------------------------------------------------------------------------------------------
 # SGEMM on tcgen05 (3xTF32): forced with sgemm.variant = 2; needs 16 B aligned operands, ld % 4 == 0
 # ---------------------------------------------------------------------------------------------

@@ -23,8 +23,8 @@ namespace trsm {
 constexpr int NB = 32;        // inverted diagonal sub-block
 constexpr int BASE = 128;     // rows of one panel-kernel launch (default recursion cut-off, and its maximum)
 constexpr int V = 64;         // right-hand-side vectors per CTA
-constexpr int XS = V + 2;     // row stride of the panel in shared memory (even: 16 B vector loads stay aligned)
-constexpr int FS = NB + 2;    // row stride of the staged F rows
+constexpr int XS = V + 4;     // row stride of the panel in shared memory (rows stay 16 B aligned for float and double)
+constexpr int FS = NB + 2;    // row stride of the staged F rows (even: 2-element vector loads stay aligned)
 constexpr int PANEL_THREADS = 256;
 
 // F is the triangular matrix normalised so that the right-hand-side vectors are columns of B (LEFT) or rows of B
@@ -82,6 +82,43 @@ __device__ __forceinline__ void cp_async_elem(T *dst_smem, const T *src, bool va
   const int bytes = valid ? (int)sizeof(T) : 0;
   if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// aligned vector loads from shared memory: 2 and 4 consecutive elements
+__device__ __forceinline__ void lds2(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void lds2(const float *p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void lds4(const double *p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void lds4(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+
+// acc[2][4] += sign * F[kk][row..row+1] (x) X[kk][vec..vec+3] over kk in [0, nk), nk a multiple of 8.  The operands of
+// eight k-steps are fetched into registers before the first FMA of the group, so the shared-memory latency of one
+// group hides behind the arithmetic of the previous one instead of stalling every step.
+template <typename T, bool SUBTRACT>
+__device__ __forceinline__ void panel_product(T (&acc)[2][4], const T *F, const T *X, int nk) {
+  constexpr int U = 8;
+  for (int kk0 = 0; kk0 < nk; kk0 += U) {
+    T f[U][2], x[U][4];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      lds2(F + (kk0 + u) * FS, f[u]);
+      lds4(X + (kk0 + u) * XS, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        if (SUBTRACT) {
+          acc[0][c] -= f[u][0] * x[u][c];
+          acc[1][c] -= f[u][1] * x[u][c];
+        } else {
+          acc[0][c] += f[u][0] * x[u][c];
+          acc[1][c] += f[u][1] * x[u][c];
+        }
+      }
+  }
 }
 
 constexpr int F_ROWS = NB * (0 + 1 + 2 + 3);  // staged rows of F over the four steps: 0 + 32 + 64 + 96
@@ -147,16 +184,7 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
     for (int a = 0; a < 2; a++)
 #pragma unroll
       for (int c = 0; c < 4; c++) acc[a][c] = alpha * sX[(r0 + row + a) * XS + vec + c];
-#pragma unroll 8
-    for (int kk = 0; kk < nk; kk++) {
-      const T f0 = F[kk * FS + row], f1 = F[kk * FS + row + 1];
-      const T *xr = sX + (k0 + kk) * XS + vec;
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        acc[0][c] -= f0 * xr[c];
-        acc[1][c] -= f1 * xr[c];
-      }
-    }
+    panel_product<T, true>(acc, F + row, sX + k0 * XS + vec, nk);
     // only their owner reads the b_sb entries -> publish R in their place
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -168,16 +196,7 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
     for (int a = 0; a < 2; a++)
 #pragma unroll
       for (int c = 0; c < 4; c++) acc[a][c] = T(0);
-#pragma unroll 8
-    for (int kk = 0; kk < NB; kk++) {
-      const T f0 = D[kk * FS + row], f1 = D[kk * FS + row + 1];
-      const T *xr = sX + (r0 + kk) * XS + vec;
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        acc[0][c] += f0 * xr[c];
-        acc[1][c] += f1 * xr[c];
-      }
-    }
+    panel_product<T, false>(acc, D + row, sX + r0 * XS + vec, NB);
     __syncthreads();  // all reads of R done
 #pragma unroll
     for (int a = 0; a < 2; a++)

@@ -339,7 +339,20 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   // Column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128.
   int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
   nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
-  const int blocks = (n + nb - 1) / nb;
+  int blocks = (n + nb - 1) / nb;
+  int col0[MAX_BLOCKS + 2], cols[MAX_BLOCKS + 2];
+  for (int j = 0; j < blocks; j++) {
+    col0[j] = j * nb;
+    cols[j] = (col0[j] + nb > n) ? n - col0[j] : nb;
+  }
+  // the last block's copy back to the host is the one transfer nothing can hide: halve it
+  if (blocks > 1 && cols[blocks - 1] >= 512) {
+    const int half = cols[blocks - 1] / 2 / 128 * 128;
+    col0[blocks] = col0[blocks - 1] + half;
+    cols[blocks] = cols[blocks - 1] - half;
+    cols[blocks - 1] = half;
+    blocks++;
+  }
   // Schedule.  Every column block needs all of A, so a plain column-block pipeline idles the GPU while A crosses
   // PCIe.  Phase 1 therefore runs the first `lead` column blocks K-panel by K-panel: panel p of A and the matching
   // pieces of those blocks are copied, then multiplied (beta, then 1) while panel p + 1 is in flight.  `lead` is
@@ -350,7 +363,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
     panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
     const double pcie = 50e9, rate = sizeof(T) == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
     const double t_a = double(bytes_a) / pcie, t_b = double(sizeof(T)) * k * nb / pcie, t_mm = 2.0 * m * nb * double(k) / rate;
-    lead = t_mm > t_b ? int(t_a / (t_mm - t_b) + 0.5) : blocks;
+    lead = t_mm > t_b ? int(t_a / (t_mm - t_b) + 0.5) : blocks;  // in units of nb columns: leading blocks are full
     if (lead < 1) lead = 1;
     // host.panels / host.lead: overrides for experiments (0 = the choice above)
     if (opt(h, "host.panels") > 0) panels = opt(h, "host.panels") < MAX_PANELS ? opt(h, "host.panels") : MAX_PANELS;
@@ -358,6 +371,20 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
     if (lead > blocks) lead = blocks;
   }
   const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
+  // K-panel table; the first panel is split in two so that the math starts after half a panel of A has landed
+  int k0s[MAX_PANELS + 2], kcs[MAX_PANELS + 2], npanels = 0;
+  for (int p0 = 0; p0 < k; p0 += kp) {
+    k0s[npanels] = p0;
+    kcs[npanels++] = p0 + kp > k ? k - p0 : kp;
+  }
+  if (panels > 1 && kcs[0] >= 1024) {
+    for (int p = npanels; p > 1; p--) { k0s[p] = k0s[p - 1]; kcs[p] = kcs[p - 1]; }
+    const int half = kcs[0] / 2 / 16 * 16;
+    k0s[1] = half;
+    kcs[1] = kcs[0] - half;
+    kcs[0] = half;
+    npanels++;
+  }
   cudaEvent_t *ev = h->host_events;
   int next_event = 1;  // [0] is the entry fence
   auto landed = [&]() {  // everything queued on the H2D stream so far is visible to the math stream after this
@@ -382,14 +409,13 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   cudaStreamWaitEvent(sin, ev[0], 0);
 
   // ---- phase 1: K-panels of A against the first `lead` column blocks (panels == 1: all of A, no blocks) ----
-  for (int p = 0; p < panels; p++) {
-    const int p0 = p * kp, kc = p0 + kp > k ? k - p0 : kp;
-    if (kc <= 0) break;
+  for (int p = 0; p < npanels; p++) {
+    const int p0 = k0s[p], kc = kcs[p];
     // A is stored m x k (N) or k x m (T): the panel is a column block or a row block
     cudaError_t e = transa == RTAT_B200_OP_N ? h2d_window(dA, A, lda, 0, p0, m, kc) : h2d_window(dA, A, lda, p0, 0, kc, m);
     if (!cuda_ok(e, "H2D A")) return RTAT_B200_STATUS_EXECUTION_FAILED;
     for (int j = 0; j < lead; j++) {
-      const int j0 = j * nb, cnt = (j0 + nb > n) ? n - j0 : nb;
+      const int j0 = col0[j], cnt = cols[j];
       // op(B) block j, K-panel p: B is stored k x n (N) or n x k (T)
       e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, p0, j0, kc, cnt) : h2d_window(dB, B, ldb, j0, p0, cnt, kc);
       if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
@@ -404,7 +430,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   }
   // ---- phase 2: whole-K column blocks ----
   for (int j = lead; j < blocks; j++) {
-    const int j0 = j * nb, cnt = (j0 + nb > n) ? n - j0 : nb;
+    const int j0 = col0[j], cnt = cols[j];
     cudaError_t e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, 0, j0, k, cnt) : h2d_window(dB, B, ldb, j0, 0, cnt, k);
     if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
     if (*beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;

@@ -21,6 +21,7 @@ void *tensor_map_encoder_raw() {
 }
 
 int ensure_arena(rtat_b200_context *h, size_t bytes) {
+  h->scratch_in_flight = true;  // the caller is about to queue work that uses the arena
   if (bytes <= h->arena_bytes) return RTAT_B200_STATUS_SUCCESS;
   if (h->arena) {
     // the arena may still be in use by work queued on the handle's stream
@@ -93,6 +94,7 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   if (h->staging) cudaFree(h->staging);
   if (h->trsm_inv) cudaFree(h->trsm_inv);
   if (h->sk_flags) cudaFree(h->sk_flags);
+  if (h->order_event) cudaEventDestroy(h->order_event);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
   for (auto e : h->host_events) if (e) cudaEventDestroy(e);
@@ -102,7 +104,20 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
 
 int rtat_b200_set_stream(rtat_b200_handle_t h, void *stream) {
   if (!h) return RTAT_B200_STATUS_NOT_INITIALIZED;
-  h->stream = static_cast<cudaStream_t>(stream);
+  cudaStream_t next = static_cast<cudaStream_t>(stream);
+  if (next != h->stream && h->scratch_in_flight) {
+    // order the new stream after whatever the old one still has queued against the handle's scratch
+    if (!h->order_event && cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_ALLOC_FAILED;
+    }
+    if (cudaEventRecord(h->order_event, h->stream) != cudaSuccess || cudaStreamWaitEvent(next, h->order_event, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    }
+    h->scratch_in_flight = false;
+  }
+  h->stream = next;
   return RTAT_B200_STATUS_SUCCESS;
 }
 

@@ -18,6 +18,11 @@ struct rtat_b200_context {
   // TRSM: inverted 32 x 32 diagonal blocks of the current call (separate from the arena, which the GEMM updates use)
   void *trsm_inv = nullptr;
   size_t trsm_inv_bytes = 0;
+  // Library-owned scratch (arena, trsm_inv, stream-K flags) is ordered by the stream the work runs on.  When the
+  // caller rebinds the handle to another stream while such work may still be queued, set_stream makes the new stream
+  // wait for it, so a later call cannot overwrite scratch an earlier one is still reading.
+  bool scratch_in_flight = false;
+  cudaEvent_t order_event = nullptr;
   // tuning knobs (rtat_b200_set_option)
   std::map<std::string, int> options;
   // introspection

@@ -320,6 +320,7 @@ static int run(rtat_b200_context *h, int side, int uplo, int trans, int diag, in
     h->trsm_inv_bytes = want;
   }
   p.inv = static_cast<const T *>(h->trsm_inv);
+  h->scratch_in_flight = true;
   trsm_diag_inverse_kernel<T><<<nblk, NB, 0, h->stream>>>(A, lda, na, p.tr, p.lower_f, p.unit, static_cast<T *>(h->trsm_inv));
   int st = check_launch(h, "trsm_diag_inverse_32");
   if (st) return st;

@@ -233,6 +233,45 @@ def test_stream_binding_and_introspection(handle):
     h2.close()
 
 
+def test_stream_rebinding_orders_the_handles_scratch():
+    """Two stream-K DGEMMs and a TRSM queued back to back on DIFFERENT streams through ONE handle share its scratch
+    (stream-K slots and flags, TRSM inverses): rtat_b200_set_stream must order the new stream after the old one."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    h = rt.Handle(stream=s1)
+    n = 1536  # 144 tiles of 128^2 on 148 SMs, 96 k-tiles: every CTA parks or merges stream-K partials
+    A1, B1, A2, B2 = (torch.rand(n * n, dtype=torch.float64, device="cuda") - 0.5 for _ in range(4))
+    C1, C2 = torch.empty_like(A1), torch.empty_like(A1)
+    T = (torch.rand(n * n, dtype=torch.float64, device="cuda") - 0.5) / 64
+    T.view(n, n).diagonal().add_(2.0)
+    X = torch.rand(n * n, dtype=torch.float64, device="cuda")
+    X0 = X.clone()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        X.copy_(X0)
+        C1.fill_(float("nan"))
+        C2.fill_(float("nan"))
+        torch.cuda.synchronize()
+        # no host synchronisation from here to the end of the round: only set_stream orders the four calls
+        h.set_stream(s1)
+        h.gemm(True, 0, 0, n, n, n, 1.0, A1, n, B1, n, 0.0, C1, n)
+        assert "streamk" in h.last_kernel()
+        h.set_stream(s2)
+        h.trsm(True, 0, 0, 0, 0, n, n, 1.0, T, n, X, n)
+        h.set_stream(s1)
+        h.gemm(True, 0, 0, n, n, n, 1.0, A2, n, B2, n, 0.0, C2, n)
+        h.set_stream(s2)
+        torch.cuda.synchronize()
+        col = lambda t: t.view(n, n).t()
+        eps = np.finfo(np.float64).eps
+        for Am, Bm, Cm in ((A1, B1, C1), (A2, B2, C2)):
+            ref, bound = col(Am) @ col(Bm), col(Am).abs() @ col(Bm).abs()
+            assert bool(torch.all((col(Cm) - ref).abs() <= 4 * n * eps * bound + eps * ref.abs()))
+        L = torch.tril(col(T))
+        res = L @ col(X) - col(X0)
+        assert bool(torch.all(res.abs() <= 4 * n * eps * (L.abs() @ col(X).abs() + col(X0).abs())))
+    h.close()
+
+
 def test_fill_uniform_matches_oracle_generator(oracle, handle):
     for dtype, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
         x = torch.empty(100003, dtype=tdt, device="cuda")

@@ -120,6 +120,40 @@ def cpu_blas_baseline(cfg, budget_s=12.0):
             "sample": f"numpy/OpenBLAS {dtype} GEMM op {ta}{tb} on a {ms}x{ns}x{ks} slab of the {m}x{n}x{k} problem, {reps} reps, all host threads"}
 
 
+def cpu_oracle_baseline(cfg, budget_s=12.0):
+    """The reference's only CPU implementation of this path — the element-wise triple loop its tests check the GPU
+    against (tests/common.h:158-193), restated in oracle/oracle.c (OpenMP over columns) — timed on a bounded block of
+    the same problem: a square block of C with the FULL k extent.  The host BLAS figure rides along as `host_blas`."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding
+
+    orc = oracle_binding.load()
+    dtype, ta, tb, m, n, k = cfg
+    npdt = np.float64 if dtype == "double" else np.float32
+    cores = os.cpu_count() or 1
+    # size the block for roughly budget_s / 2 at ~0.25 GFLOP/s per core
+    side = int(max(64, min(m, n, (0.5 * budget_s * 0.25e9 * cores / (2.0 * k)) ** 0.5)) // 64 * 64) or min(m, n)
+    ms, ns = min(m, side), min(n, side)
+    ar, ac = (k, ms) if ta == "T" else (ms, k)
+    br, bc = (ns, k) if tb == "T" else (k, ns)
+    A, B = orc.fill(ar * ac, 1, npdt), orc.fill(br * bc, 2, npdt)
+    Cm = np.zeros(ms * ns, dtype=npdt)
+    t0, reps = time.perf_counter(), 0
+    while True:
+        orc.gemm(int(ta == "T"), int(tb == "T"), ms, ns, k, 1.0, A, ar, B, br, 0.0, Cm, ms)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s / 2 or reps >= 3:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    out = {"value": 2.0 * ms * ns * k / dt * 1e-12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+           "sample": f"oracle_{'d' if dtype == 'double' else 's'}gemm (the reference's test_gemm triple loop, OpenMP) on the {ms}x{ns} leading block of C "
+                     f"of the {m}x{n}x{k} op {ta}{tb} problem, full k, {reps} reps"}
+    out["host_blas"] = {k2: v for k2, v in cpu_blas_baseline(cfg, budget_s=budget_s / 2).items() if k2 in ("value", "unit", "cores", "sample")}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args, cfg_name, cfg, rank, world):
     """The reference's own driver on this GPU (cuBLAS-backed executor), best plan."""
@@ -406,7 +440,7 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_blas_baseline(cfg)
+            line["cpu_baseline"] = cpu_oracle_baseline(cfg)
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()

@@ -42,7 +42,10 @@ namespace rtat_b200 {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 4;
+#ifndef RTAT_SGEMM_STAGES
+#define RTAT_SGEMM_STAGES 4  // probe builds override this (probe/build_variants.sh)
+#endif
+constexpr int STAGES = RTAT_SGEMM_STAGES;
 constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB: one operand tile
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;        // A raw, B raw -> big, B small
 constexpr int TMEM_A0 = 256;                       // first TMEM column of the A staging slots (64 per stage)

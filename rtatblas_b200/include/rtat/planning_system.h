@@ -44,6 +44,7 @@ class Planning_System {
   Executor_Type executor;
   const Option_Filter<Key, Opts> opt_filter;
   size_t tests_until_converge = 1;
+  float default_preference = 0.02f;  // relative margin within which the default plan is kept (0 = strict minimum)
   std::map<Key, Opts> converged_plans;
   Device_Timer::Mode sync_mode = Device_Timer::ASYNCHRONOUS;
 
@@ -73,12 +74,24 @@ class Planning_System {
       const float mean = float(std::accumulate(ts.begin(), ts.end(), 0.0) / ts.size());
       if (mean < best_ms) { best = opts; best_ms = mean; }
     }
+    // Event timings of short problems jitter by a few per cent; a plan that spends extra passes and workspace must win
+    // by more than that to displace the default (fully fused) plan.  The reference takes the strict minimum.
+    if (default_preference > 0.f) {
+      const Opts dflt = Opts::default_opts();
+      auto it = timings.find(dflt);
+      if (it != timings.end() && it->second.size() > 0) {
+        const std::vector<float> &ts = it->second.get_times();
+        const float mean = float(std::accumulate(ts.begin(), ts.end(), 0.0) / ts.size());
+        if (mean <= best_ms * (1.f + default_preference)) best = dflt;
+      }
+    }
     converged_plans.insert_or_assign(key, best);
     return best;
   }
 
   void set_sync_mode(Device_Timer::Mode mode) { sync_mode = mode; }
   void set_tests_until_converge(size_t n) { tests_until_converge = n ? n : 1; }
+  void set_default_preference(float margin) { default_preference = margin > 0.f ? margin : 0.f; }
 
   // `s` must be the stream bound to params.handle (timing events are recorded on it).
   void execute(Params params, Opts opts, Workspace space, Stream s) {

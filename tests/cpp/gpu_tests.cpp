@@ -323,6 +323,67 @@ TEST(Planning_Test, Dummy_Planner) {
   }
 }
 
+// A plan space whose timings are known by construction: plan i streams work[i] columns through geam.
+namespace {
+struct Timed_Params {
+  gpu::blasHandle_t handle;
+  Matrix<double> src, dst;
+};
+struct Timed_Key {
+  int id;
+  Timed_Key(const Timed_Params &) : id(0) {}
+  bool operator<(const Timed_Key &o) const { return id < o.id; }
+};
+struct Timed_Op : MatrixOp<double> {
+  Timed_Params p;
+  size_t cols;
+  Timed_Op(Timed_Params p, size_t cols) : MatrixOp<double>({}), p(p), cols(cols) {}
+  Matrix<double> execute(gpu::blasHandle_t h, Workspace, Workspace) override {
+    const size_t m = p.src.dims().m;
+    Matrix<double> a(Workspace(p.src.ptr(), m * cols), m, cols, m), b(Workspace(p.dst.ptr(), m * cols), m, cols, m);
+    blas_status_check(gpuTgeam<double>(h, false, false, a, b, b, 1.0, 0.0), "Timed_Op: geam");
+    return b;
+  }
+  size_t output_space_req() const override { return 0; }
+  MatrixDims dims() const override { return p.dst.dims(); }
+};
+struct Timed_Opts {
+  int i;
+  Timed_Opts(int i = 0) : i(i) {}
+  operator std::string() const { return std::to_string(i); }
+  static std::vector<Timed_Opts> enumerate() { return {Timed_Opts(0), Timed_Opts(1), Timed_Opts(2)}; }
+  bool operator<(const Timed_Opts &o) const { return i < o.i; }
+  static Timed_Opts default_opts() { return Timed_Opts(0); }
+  // plan 0 (the default) moves 4096 columns, plan 1 is 30 % cheaper, plan 2 twice as expensive
+  std::unique_ptr<MatrixOp<double>> form_operation(Timed_Params p) {
+    const size_t cols[3] = {4096, 2867, 8192};
+    return std::make_unique<Timed_Op>(p, cols[i]);
+  }
+};
+inline rtat::Json to_json(const Timed_Key &k) { return rtat::Json(k.id); }
+inline rtat::Json to_json(const Timed_Opts &o) { return rtat::Json(o.i); }
+struct Timed_Executor : Executor<Timed_Params, Timed_Key, Timed_Opts> {
+  void warmup(Timed_Params p, Timed_Opts, Stream) override { Timed_Op(p, 64).execute(p.handle, Workspace(), Workspace()); }
+};
+}  // namespace
+
+TEST(Planning_Test, Default_Plan_Is_Kept_Within_The_Noise_Margin) {
+  BLAS_Fixture f;
+  const size_t m = 4096, n = 8192;
+  ManagedWorkspace src(m * n * sizeof(double)), dst(m * n * sizeof(double));
+  Timed_Params p{f.handle, Matrix<double>(src, m, n, m), Matrix<double>(dst, m, n, m)};
+  auto converge = [&](float margin) {
+    Planning_System<Timed_Executor> planner;
+    planner.set_default_preference(margin);
+    planner.set_tests_until_converge(3);
+    for (int i = 0; i < 9; i++) planner.execute(p, planner.create_plan(p), Workspace(), f.s);
+    return planner.create_plan(p).i;
+  };
+  EXPECT_EQ(converge(0.f), 1);     // strict minimum (the reference's rule): the 30 % cheaper plan
+  EXPECT_EQ(converge(0.02f), 1);   // the default margin does not hide a real 30 % win
+  EXPECT_EQ(converge(0.60f), 0);   // within the margin the default plan is kept
+}
+
 TEST(Planning_Test, GEMM_Correctness) {
   BLAS_Fixture f;
   GEMM_Planner planner;

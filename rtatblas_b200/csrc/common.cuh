@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <atomic>
 #include <map>
 #include "../../include/rtat_b200.h"
 
@@ -61,6 +62,21 @@ inline int check_launch(rtat_b200_context *h, const char *kernel, int nlaunch = 
     (void)cudaGetLastError();
     return RTAT_B200_STATUS_EXECUTION_FAILED;
   }
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel, device).  `done` is a per-call-site
+// bit mask of device ordinals (static std::atomic<uint64_t> next to the launch); racing threads may both make the
+// (idempotent) runtime call.  Devices >= 64 are simply configured on every launch.
+template <typename Kernel>
+inline int configure_dynamic_smem(Kernel kernel, size_t bytes, int device, std::atomic<uint64_t> &done) {
+  const uint64_t bit = device >= 0 && device < 64 ? uint64_t(1) << device : 0;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return RTAT_B200_STATUS_SUCCESS;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_INTERNAL_ERROR;
+  }
+  if (bit) done.fetch_or(bit, std::memory_order_release);
   return RTAT_B200_STATUS_SUCCESS;
 }
 

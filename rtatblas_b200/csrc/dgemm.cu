@@ -194,14 +194,8 @@ static int launch_cfg(rtat_b200_context *h, DgemmParams &p, const char *name) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t smem = sizeof(double) * STAGES * (TileA::ELEMS + TileB::ELEMS);
   auto kern = dgemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, ALIGNED>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return RTAT_B200_STATUS_INTERNAL_ERROR;
-    }
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // per template instantiation
+  if (int st = configure_dynamic_smem(kern, smem, h->device, configured)) return st;
   p.tiles_m = (p.m + BM - 1) / BM;
   p.tiles_n = (p.n + BN - 1) / BN;
   long long tiles = (long long)p.tiles_m * p.tiles_n;

@@ -518,14 +518,8 @@ static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtenso
   auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
   constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return RTAT_B200_STATUS_INTERNAL_ERROR;
-    }
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // per template instantiation
+  if (int st = configure_dynamic_smem(kern, SMEM_BYTES, h->device, configured)) return st;
   int threads = (CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32;
   kern<<<grid, threads, SMEM_BYTES, h->stream>>>(ma, mb, p);
   return check_launch(h, name);

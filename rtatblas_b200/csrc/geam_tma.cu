@@ -246,23 +246,14 @@ int geam_transpose_tma(rtat_b200_context *h, int m, int n, T alpha, const T *A, 
   const size_t smem = (size_t)(IN_STAGES + OUT_STAGES) * tile_bytes + 1024 + 256;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
   int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  auto launch = [&](auto kern) {
-    // (both instantiations share one function-pointer type, so "configured" must be tracked per pointer)
-    static const void *configured[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool seen = false;
-    for (auto c : configured) seen = seen || c == (const void *)kern;
-    if (!seen) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return (int)RTAT_B200_STATUS_INTERNAL_ERROR;
-      }
-      for (auto &c : configured)
-        if (!c) { c = (const void *)kern; break; }
-    }
+  // one mask per instantiation (the two kernels share a function-pointer type, so a generic lambda would share one)
+  static std::atomic<uint64_t> configured[2];
+  auto launch = [&](auto kern, std::atomic<uint64_t> &done) {
+    if (int st = configure_dynamic_smem(kern, smem, h->device, done)) return st;
     kern<<<grid, THREADS, smem, h->stream>>>(ma, mb, mc, p);
     return check_launch(h, use_b ? "geam_transpose_tma_accumulate" : "geam_transpose_tma");
   };
-  return use_b ? launch(geam_transpose_tma_kernel<T, true>) : launch(geam_transpose_tma_kernel<T, false>);
+  return use_b ? launch(geam_transpose_tma_kernel<T, true>, configured[1]) : launch(geam_transpose_tma_kernel<T, false>, configured[0]);
 }
 
 template bool geam_transpose_tma_supported<double>(int, int, const double *, int, const double *, int, const double *, int, bool);

@@ -442,14 +442,8 @@ __global__ void split_tf32_kernel(const float *__restrict__ B, int ldb, int rows
 template <bool TA, bool TB, bool PRESPLIT>
 static int launch(rtat_b200_context *h, const Params &p, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbs) {
   auto kern = sgemm_tcgen05_kernel<TA, TB, PRESPLIT>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return RTAT_B200_STATUS_INTERNAL_ERROR;
-    }
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // per template instantiation
+  if (int st = configure_dynamic_smem(kern, SMEM_BYTES, h->device, configured)) return st;
   int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, mbs, p);
   if (p.tri) return check_launch(h, PRESPLIT ? "ssyrk_tcgen05_3xtf32_128x128x32_presplitB" : "ssyrk_tcgen05_3xtf32_128x128x32", PRESPLIT ? 2 : 1);

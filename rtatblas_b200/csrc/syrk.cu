@@ -17,39 +17,22 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
 int sgemm_tri(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha,
               const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc, int tri);
 
-// C(triangle) = beta * C(triangle); beta == 0 stores zeros without reading (NaN-safe)
+// C(triangle) = beta * C(triangle); beta == 0 stores zeros without reading (NaN-safe).  blockIdx.y strides over columns.
 template <typename T>
 __global__ void tri_scale_kernel(T *C, int ldc, int n, T beta, int lower) {
-  const int col = blockIdx.y;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n || (lower ? row < col : row > col)) return;
-  T *c = C + (size_t)col * ldc + row;
-  *c = beta == T(0) ? T(0) : beta * *c;
+  if (row >= n) return;
+  for (int col = blockIdx.y; col < n; col += gridDim.y) {
+    if (lower ? row < col : row > col) continue;
+    T *c = C + (size_t)col * ldc + row;
+    *c = beta == T(0) ? T(0) : beta * *c;
+  }
 }
 
 template <typename T>
 static int tri_scale(rtat_b200_context *h, int uplo, int n, T beta, T *C, int ldc) {
   if (beta == T(1)) return RTAT_B200_STATUS_SUCCESS;
-  if (n > 65535) {
-    // blockIdx.y carries the column (limit 65535): scale square diagonal blocks with the triangle kernel and the
-    // rectangles beside them with geam
-    for (int c0 = 0; c0 < n; c0 += 32768) {
-      const int nb = n - c0 < 32768 ? n - c0 : 32768;
-      dim3 grid((nb + 255) / 256, nb);
-      tri_scale_kernel<T><<<grid, 256, 0, h->stream>>>(C + (size_t)c0 * ldc + c0, ldc, nb, beta, uplo == RTAT_B200_FILL_LOWER);
-      int st = check_launch(h, "syrk_tri_scale");
-      if (st) return st;
-      // the full rectangle below (lower) or above (upper) the diagonal block
-      const int rest = uplo == RTAT_B200_FILL_LOWER ? n - c0 - nb : c0;
-      if (rest > 0) {
-        T *R = uplo == RTAT_B200_FILL_LOWER ? C + (size_t)c0 * ldc + c0 + nb : C + (size_t)c0 * ldc;
-        st = geam<T>(h, RTAT_B200_OP_N, RTAT_B200_OP_N, rest, nb, T(0), nullptr, ldc, beta, R, ldc, R, ldc);
-        if (st) return st;
-      }
-    }
-    return RTAT_B200_STATUS_SUCCESS;
-  }
-  dim3 grid((n + 255) / 256, n);
+  dim3 grid((n + 255) / 256, n < 65535 ? n : 65535);
   tri_scale_kernel<T><<<grid, 256, 0, h->stream>>>(C, ldc, n, beta, uplo == RTAT_B200_FILL_LOWER);
   return check_launch(h, "syrk_tri_scale");
 }

@@ -240,14 +240,8 @@ struct Problem {
 template <typename T, bool LEFT>
 static int launch_panel(const Problem<T> &p, int o, int s, T alpha) {
   auto kern = trsm_panel_kernel<T, LEFT>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_bytes<T>()) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return RTAT_B200_STATUS_INTERNAL_ERROR;
-    }
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // per template instantiation
+  if (int st = configure_dynamic_smem(kern, panel_smem_bytes<T>(), p.h->device, configured)) return st;
   const int nvec = LEFT ? p.n : p.m;
   const T *Ablk = p.A + (size_t)o * p.lda + o;
   T *Bblk = LEFT ? p.B + o : p.B + (size_t)o * p.ldb;

@@ -25,7 +25,7 @@ struct rtat_b200_context {
   bool scratch_in_flight = false;
   cudaEvent_t order_event = nullptr;
   // tuning knobs (rtat_b200_set_option)
-  std::map<std::string, int> options;
+  std::map<std::string, int, std::less<>> options;  // transparent comparator: lookups by const char* build no std::string
   // introspection
   const char *last_kernel = "none";
   uint64_t launches = 0;

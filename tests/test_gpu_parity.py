@@ -336,6 +336,15 @@ def test_dgemm_config5_column_block(handle):
     _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_extreme_aspect_ratios(handle, dtype):
+    """Degenerate-looking shapes stress the schedules rather than the math: one tile with a very long k (every CTA of the
+    stream-K grid contributes to a single tile), vectors, and single rows / columns of tiles."""
+    for (ta, tb, m, n, k) in [(0, 0, 1, 1, 200000), (1, 0, 128, 128, 131072), (0, 1, 100000, 1, 3), (0, 0, 3, 100000, 2),
+                              (1, 1, 1, 70000, 33), (0, 0, 40000, 130, 1)]:
+        _full_size_vs_cublas(handle, dtype, ta, tb, m, n, k, 9100 + m % 97)
+
+
 # ---------------------------------------------------------------------------------------------
 # host-buffer entry points (what bench.py's e2e number times)
 # ---------------------------------------------------------------------------------------------

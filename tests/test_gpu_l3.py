@@ -277,6 +277,20 @@ def test_dtrsm_recursion_cutoffs(oracle, handle, base):
         handle.set_option("trsm.base", 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_syrk_trsm_extreme_aspect_ratios(oracle, handle, dtype):
+    """One tile with a very long k (the whole stream-K grid feeds it), a rank-1/2 update of a large triangle, a single
+    right-hand side against a deep recursion, and a 1 x 1 triangle against thousands of right-hand sides."""
+    _syrk_case(oracle, handle, dtype, 1, 0, 64, 60000, 1.0, 0.0, 2000)
+    _syrk_case(oracle, handle, dtype, 0, 1, 96, 40001, -1.0, 1.0, 2001)
+    _syrk_case(oracle, handle, dtype, 1, 1, 1500, 2, 0.5, 2.0, 2002)
+    _syrk_case(oracle, handle, dtype, 0, 0, 1300, 1, 1.0, 0.0, 2003)
+    _trsm_case(oracle, handle, dtype, 1, 1, 0, 0, 1100, 1, 1.0, 2010)
+    _trsm_case(oracle, handle, dtype, 0, 0, 1, 1, 1, 1100, -2.0, 2011)
+    _trsm_case(oracle, handle, dtype, 1, 0, 1, 0, 1, 5000, 1.0, 2012)
+    _trsm_case(oracle, handle, dtype, 0, 1, 0, 1, 5000, 1, 0.5, 2013)
+
+
 def test_strsm_mid_size(oracle, handle):
     for left, lower, trans in [(1, 1, 0), (0, 0, 1), (1, 0, 0), (0, 1, 1)]:
         _trsm_case(oracle, handle, np.float32, left, lower, trans, 0, 520, 384, 1.0, 1300)

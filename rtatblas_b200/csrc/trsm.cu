@@ -24,8 +24,9 @@ constexpr int NB = 32;        // inverted diagonal sub-block
 constexpr int BASE = 128;     // rows of one panel-kernel launch (default recursion cut-off, and its maximum)
 constexpr int V = 64;         // right-hand-side vectors per CTA
 constexpr int XS = V + 4;     // row stride of the panel in shared memory (rows stay 16 B aligned for float and double)
-constexpr int FS = NB + 2;    // row stride of the staged F rows (even: 2-element vector loads stay aligned)
-constexpr int PANEL_THREADS = 256;
+constexpr int FS = NB + 4;    // row stride of the staged F rows (4-element vector loads stay 16 B aligned for float and double)
+constexpr int PANEL_THREADS = 256;   // all of them stage and store; the first COMPUTE_THREADS own the 32 x 64 sub-block results
+constexpr int COMPUTE_THREADS = 128;
 
 // F is the triangular matrix normalised so that the right-hand-side vectors are columns of B (LEFT) or rows of B
 // (!LEFT, where F = op(A)^T):  F(i, j) = tr ? A(j, i) : A(i, j);  lower_f: F is lower triangular.
@@ -84,40 +85,36 @@ __device__ __forceinline__ void cp_async_elem(T *dst_smem, const T *src, bool va
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-// aligned vector loads from shared memory: 2 and 4 consecutive elements
-__device__ __forceinline__ void lds2(const double *p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y; }
-__device__ __forceinline__ void lds2(const float *p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+// aligned vector load from shared memory: 4 consecutive elements
 __device__ __forceinline__ void lds4(const double *p, double (&v)[4]) {
   const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 __device__ __forceinline__ void lds4(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 
-// acc[2][4] += sign * F[kk][row..row+1] (x) X[kk][vec..vec+3] over kk in [0, nk), nk a multiple of 8.  The operands of
-// eight k-steps are fetched into registers before the first FMA of the group, so the shared-memory latency of one
-// group hides behind the arithmetic of the previous one instead of stalling every step.
+// acc[4][4] += sign * F[kk][row..row+3] (x) X[kk][vec..vec+3] over kk in [0, nk), nk a multiple of 8.  The operands of
+// eight k-steps are fetched into registers before the first FMA of the group, and each thread carries 16 independent
+// accumulators: one warp per scheduler then has enough FMAs in flight to cover both the shared-memory and the FP64
+// latency (a 2 x 4 patch on twice the threads was latency-bound at a third of the pipe's rate).
 template <typename T, bool SUBTRACT>
-__device__ __forceinline__ void panel_product(T (&acc)[2][4], const T *F, const T *X, int nk) {
+__device__ __forceinline__ void panel_product(T (&acc)[4][4], const T *F, const T *X, int nk) {
   constexpr int U = 8;
   for (int kk0 = 0; kk0 < nk; kk0 += U) {
-    T f[U][2], x[U][4];
+    T f[U][4], x[U][4];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      lds2(F + (kk0 + u) * FS, f[u]);
+      lds4(F + (kk0 + u) * FS, f[u]);
       lds4(X + (kk0 + u) * XS, x[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        if (SUBTRACT) {
-          acc[0][c] -= f[u][0] * x[u][c];
-          acc[1][c] -= f[u][1] * x[u][c];
-        } else {
-          acc[0][c] += f[u][0] * x[u][c];
-          acc[1][c] += f[u][1] * x[u][c];
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (SUBTRACT) acc[a][c] -= f[u][a] * x[u][c];
+          else acc[a][c] += f[u][a] * x[u][c];
         }
-      }
   }
 }
 
@@ -138,10 +135,10 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
   const int v0 = blockIdx.x * V;
   const int nsub = (s + NB - 1) / NB, rows = nsub * NB;
 
-  // ---- one burst of asynchronous copies ----
+  // ---- one burst of asynchronous copies (index arithmetic is shifts and masks only) ----
   if (LEFT) {  // r fastest: columns of B are contiguous
-    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
-      const int r = idx % rows, v = idx / rows;
+    for (int idx = tid; idx < BASE * V; idx += PANEL_THREADS) {
+      const int r = idx % BASE, v = idx / BASE;
       const bool ok = r < s && v0 + v < nvec;
       cp_async_elem(sX + r * XS + v, ok ? B + (size_t)(v0 + v) * ldb + r : B, ok);
     }
@@ -157,7 +154,9 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
     const int k0 = lower_f ? 0 : r0 + NB, nk = step * NB;  // the rows solved before this step
     T *dst = sF + (NB * step * (step - 1) / 2) * FS;
     for (int idx = tid; idx < nk * NB; idx += PANEL_THREADS) {
-      const int i = tr ? idx / nk : idx % NB, kk = tr ? idx % nk : idx / NB;  // fastest index = A's contiguous one
+      // fastest index = A's contiguous one: i for F(i, k) = A(i, k), k (in runs of NB) for F(i, k) = A(k, i)
+      const int lo = idx % NB, mid = (idx / NB) % NB, hi = idx / (NB * NB);
+      const int i = tr ? mid : lo, kk = tr ? hi * NB + lo : idx / NB;
       const int gi = r0 + i, gk = k0 + kk;
       const bool ok = gi < s && gk < s;
       cp_async_elem(dst + kk * FS + i, ok ? (tr ? A + (size_t)gi * lda + gk : A + (size_t)gk * lda + gi) : A, ok);
@@ -168,47 +167,56 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
 
-  // thread -> 2 rows x 4 vectors of the 32 x 64 sub-block result
-  const int warp = tid / 32, lane = tid % 32;
-  const int row = 16 * (warp / 4) + 2 * (lane / 4);   // 0..30, even
-  const int vec = 16 * (warp % 4) + 4 * (lane % 4);   // 0..60, multiple of 4
+  // compute thread -> 4 rows x 4 vectors of the 32 x 64 sub-block result; a warp spans all 32 rows and 16 vectors
+  const bool computes = tid < COMPUTE_THREADS;
+  const int lane = tid % 32;
+  const int row = 4 * (lane / 4);                            // 0..28
+  const int vec = 16 * ((tid / 32) % 4) + 4 * (lane % 4);    // 0..60
 
   for (int step = 0; step < nsub; step++) {
     const int sb = lower_f ? step : nsub - 1 - step, r0 = sb * NB;
     const int k0 = lower_f ? 0 : r0 + NB, nk = step * NB;
     const T *F = sF + (NB * step * (step - 1) / 2) * FS;
     const T *D = sD + sb * NB * FS;
-    // R = alpha b_sb - F[sb, solved] X[solved]   (alpha was folded into the solved X already)
-    T acc[2][4];
+    T acc[4][4];
+    if (computes) {
+      // R = alpha b_sb - F[sb, solved] X[solved]   (alpha was folded into the solved X already)
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+      for (int a = 0; a < 4; a++) {
+        lds4(sX + (r0 + row + a) * XS + vec, acc[a]);
 #pragma unroll
-      for (int c = 0; c < 4; c++) acc[a][c] = alpha * sX[(r0 + row + a) * XS + vec + c];
-    panel_product<T, true>(acc, F + row, sX + k0 * XS + vec, nk);
-    // only their owner reads the b_sb entries -> publish R in their place
+        for (int c = 0; c < 4; c++) acc[a][c] *= alpha;
+      }
+      panel_product<T, true>(acc, F + row, sX + k0 * XS + vec, nk);
+      // only their owner reads the b_sb entries -> publish R in their place
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
+        for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
+    }
     __syncthreads();
-    // X_sb = Finv_sb R
+    if (computes) {
+      // X_sb = Finv_sb R
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) acc[a][c] = T(0);
-    panel_product<T, false>(acc, D + row, sX + r0 * XS + vec, NB);
+        for (int c = 0; c < 4; c++) acc[a][c] = T(0);
+      panel_product<T, false>(acc, D + row, sX + r0 * XS + vec, NB);
+    }
     __syncthreads();  // all reads of R done
+    if (computes) {
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+      for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
+        for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
+    }
     __syncthreads();  // X_sb visible to the next step
   }
 
   // ---- panel out ----
   if (LEFT) {
-    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
-      const int r = idx % rows, v = idx / rows;
+    for (int idx = tid; idx < BASE * V; idx += PANEL_THREADS) {
+      const int r = idx % BASE, v = idx / BASE;
       if (r < s && v0 + v < nvec) B[(size_t)(v0 + v) * ldb + r] = sX[r * XS + v];
     }
   } else {

@@ -122,7 +122,8 @@ constexpr int F_ROWS = NB * (0 + 1 + 2 + 3);  // staged rows of F over the four 
 
 // Solves F x = alpha b for V vectors per CTA, F = the s x s (s <= BASE) diagonal block at A whose NB x NB diagonal
 // sub-block inverses start at `inv`.  Everything the CTA needs — the panel, the strictly triangular part of F in
-// step order, the four inverses — is fetched with one burst of cp.async at entry, so global latency is paid once.
+// step order, the four inverses — is requested with cp.async at entry, one commit group per step, so the global
+// latency is paid once and later steps' data arrives behind the earlier steps' arithmetic.
 template <typename T, bool LEFT>
 __global__ void __launch_bounds__(PANEL_THREADS)
 trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nvec, T alpha, int tr, int lower_f,
@@ -135,22 +136,25 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
   const int v0 = blockIdx.x * V;
   const int nsub = (s + NB - 1) / NB, rows = nsub * NB;
 
-  // ---- one burst of asynchronous copies (index arithmetic is shifts and masks only) ----
-  if (LEFT) {  // r fastest: columns of B are contiguous
-    for (int idx = tid; idx < BASE * V; idx += PANEL_THREADS) {
-      const int r = idx % BASE, v = idx / BASE;
-      const bool ok = r < s && v0 + v < nvec;
-      cp_async_elem(sX + r * XS + v, ok ? B + (size_t)(v0 + v) * ldb + r : B, ok);
-    }
-  } else {     // v fastest: rows of B run along its contiguous dimension
-    for (int idx = tid; idx < rows * V; idx += PANEL_THREADS) {
-      const int v = idx % V, r = idx / V;
-      const bool ok = r < s && v0 + v < nvec;
-      cp_async_elem(sX + r * XS + v, ok ? B + (size_t)r * ldb + v0 + v : B, ok);
-    }
-  }
-  for (int step = 1; step < nsub; step++) {
+  // ---- asynchronous copies, one commit group per step: what step t needs (its 32 panel rows, its inverse, its rows of F)
+  // lands while the steps before it compute.  Index arithmetic is shifts and masks only.
+  for (int step = 0; step < nsub; step++) {
     const int sb = lower_f ? step : nsub - 1 - step, r0 = sb * NB;
+    if (LEFT) {  // r fastest: columns of B are contiguous
+      for (int idx = tid; idx < NB * V; idx += PANEL_THREADS) {
+        const int r = r0 + idx % NB, v = idx / NB;
+        const bool ok = r < s && v0 + v < nvec;
+        cp_async_elem(sX + r * XS + v, ok ? B + (size_t)(v0 + v) * ldb + r : B, ok);
+      }
+    } else {     // v fastest: rows of B run along its contiguous dimension
+      for (int idx = tid; idx < NB * V; idx += PANEL_THREADS) {
+        const int v = idx % V, r = r0 + idx / V;
+        const bool ok = r < s && v0 + v < nvec;
+        cp_async_elem(sX + r * XS + v, ok ? B + (size_t)r * ldb + v0 + v : B, ok);
+      }
+    }
+    for (int idx = tid; idx < NB * NB; idx += PANEL_THREADS)
+      cp_async_elem(sD + (sb * NB + idx / NB) * FS + idx % NB, inv + (size_t)sb * NB * NB + idx, true);
     const int k0 = lower_f ? 0 : r0 + NB, nk = step * NB;  // the rows solved before this step
     T *dst = sF + (NB * step * (step - 1) / 2) * FS;
     for (int idx = tid; idx < nk * NB; idx += PANEL_THREADS) {
@@ -161,10 +165,16 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
       const bool ok = gi < s && gk < s;
       cp_async_elem(dst + kk * FS + i, ok ? (tr ? A + (size_t)gi * lda + gk : A + (size_t)gk * lda + gi) : A, ok);
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
-  for (int idx = tid; idx < nsub * NB * NB; idx += PANEL_THREADS)
-    cp_async_elem(sD + (idx / NB) * FS + idx % NB, inv + idx, true);
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  // blocks until at most `pending` of this thread's commit groups are still in flight
+  auto wait_groups = [](int pending) {
+    if (pending >= 3) asm volatile("cp.async.wait_group 3;\n" ::: "memory");
+    else if (pending == 2) asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  };
+  wait_groups(nsub - 1);
   __syncthreads();
 
   // compute thread -> 4 rows x 4 vectors of the 32 x 64 sub-block result; a warp spans all 32 rows and 16 vectors
@@ -210,7 +220,8 @@ trsm_panel_kernel(const T *__restrict__ A, int lda, T *B, int ldb, int s, int nv
 #pragma unroll
         for (int c = 0; c < 4; c++) sX[(r0 + row + a) * XS + vec + c] = acc[a][c];
     }
-    __syncthreads();  // X_sb visible to the next step
+    wait_groups(nsub - 2 - step);  // the next step's group (no-op after the last one)
+    __syncthreads();               // X_sb and the next step's staged data visible to everyone
   }
 
   // ---- panel out ----

@@ -402,10 +402,11 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   }
   cudaEvent_t *ev = h->host_events;
   int next_event = 1;  // [0] is the entry fence
-  auto landed = [&]() {  // everything queued on the H2D stream so far is visible to the math stream after this
+  // everything queued on the H2D stream so far is visible to the math stream after this.  A failed record / wait would
+  // silently drop an ordering edge of the pipeline, so every one is checked.
+  auto landed = [&]() {
     cudaEvent_t e = ev[next_event++];
-    cudaEventRecord(e, sin);
-    cudaStreamWaitEvent(s, e, 0);
+    return cuda_ok(cudaEventRecord(e, sin), "record H2D") && cuda_ok(cudaStreamWaitEvent(s, e, 0), "wait for H2D");
   };
   // stored element (row, col) of a column-major host/device pair -> 2-D copy of a rows x cols window
   auto h2d_window = [&](T *dst, const T *src, int ld, size_t row0, size_t col0, size_t rows, size_t cols) {
@@ -415,13 +416,12 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   };
   auto d2h_block = [&](int j0, int cnt) {  // only the m x cnt window (ldc padding rows on the host are left untouched)
     cudaEvent_t e = ev[next_event++];
-    cudaEventRecord(e, s);
-    cudaStreamWaitEvent(sout, e, 0);
-    return cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
+    return cuda_ok(cudaEventRecord(e, s), "record GEMM") && cuda_ok(cudaStreamWaitEvent(sout, e, 0), "wait for GEMM") &&
+           cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
                                      cudaMemcpyDeviceToHost, sout), "D2H C");
   };
   if (!cuda_ok(cudaEventRecord(ev[0], s), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-  cudaStreamWaitEvent(sin, ev[0], 0);
+  if (!cuda_ok(cudaStreamWaitEvent(sin, ev[0], 0), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
 
   // ---- phase 1: K-panels of A against the first `lead` column blocks (panels == 1: all of A, no blocks) ----
   for (int p = 0; p < npanels; p++) {
@@ -435,7 +435,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
       e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, p0, j0, kc, cnt) : h2d_window(dB, B, ldb, j0, p0, cnt, kc);
       if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
       if (p == 0 && *beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-      landed();
+      if (!landed()) return RTAT_B200_STATUS_EXECUTION_FAILED;
       const T *Ap = transa == RTAT_B200_OP_N ? dA + (size_t)p0 * lda : dA + p0;
       const T *Bjp = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb + p0 : dB + (size_t)p0 * ldb + j0;
       st = gemm_fn(h, transa, transb, m, cnt, kc, *alpha, Ap, lda, Bjp, ldb, p == 0 ? *beta : T(1), dC + (size_t)j0 * ldc, ldc);
@@ -449,7 +449,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
     cudaError_t e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, 0, j0, k, cnt) : h2d_window(dB, B, ldb, j0, 0, cnt, k);
     if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
     if (*beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    landed();
+    if (!landed()) return RTAT_B200_STATUS_EXECUTION_FAILED;
     const T *Bj = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb : dB + j0;
     st = gemm_fn(h, transa, transb, m, cnt, k, *alpha, dA, lda, Bj, ldb, *beta, dC + (size_t)j0 * ldc, ldc);
     if (st) return st;

@@ -148,7 +148,15 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
     else rtat_b200_mg_panel(k, panels, p, &k0, &kw);
     if (kw <= 0) continue;
     // ---- copy engine: panel p of A, root -> local stage (waits until last call's GEMM has read the slot)
-    if (mg->consumed_valid) cudaStreamWaitEvent(mg->copy_stream, mg->consumed[p], 0);
+    // a failed record / wait would silently drop an ordering edge of the pipeline, so every one is checked
+    auto sync_ok = [](cudaError_t err, const char *what) {
+      if (err == cudaSuccess) return true;
+      fprintf(stderr, "rtat_b200_mg: %s failed: %s\n", what, cudaGetErrorString(err));
+      (void)cudaGetLastError();
+      return false;
+    };
+    if (mg->consumed_valid && !sync_ok(cudaStreamWaitEvent(mg->copy_stream, mg->consumed[p], 0), "wait for the slot"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
     cudaError_t e;
     if (!ta) {
       // A is m x k: panel = columns [k0, k0 + kw), lda*kw contiguous elements when lda == m, else a strided block
@@ -164,15 +172,16 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
       (void)cudaGetLastError();
       return RTAT_B200_STATUS_EXECUTION_FAILED;
     }
-    cudaEventRecord(mg->landed[p], mg->copy_stream);
     // ---- math: C += alpha * op(A)[:, panel] * op(B)[panel, :]
-    cudaStreamWaitEvent(h->stream, mg->landed[p], 0);
+    if (!sync_ok(cudaEventRecord(mg->landed[p], mg->copy_stream), "record panel landed") ||
+        !sync_ok(cudaStreamWaitEvent(h->stream, mg->landed[p], 0), "wait for the panel"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
     const double *Ap = ta ? A_stage + k0 : A_stage + (size_t)k0 * lda;
     const double *Bp = tb ? B_loc + (size_t)k0 * ldb : B_loc + k0;
     int st = rtat_b200_dgemm(h, transa, transb, m, n_loc, kw, alpha, Ap, lda, Bp, ldb, first_gemm ? beta : &one, C_loc, ldc);
     first_gemm = false;
     if (st) return st;
-    cudaEventRecord(mg->consumed[p], h->stream);
+    if (!sync_ok(cudaEventRecord(mg->consumed[p], h->stream), "record panel consumed")) return RTAT_B200_STATUS_EXECUTION_FAILED;
   }
   mg->consumed_valid = true;
   return RTAT_B200_STATUS_SUCCESS;

@@ -388,8 +388,41 @@ def main():
         torch.cuda.synchronize()
         e_steps = max(1, min(args.steps, 3))
 
-        def e2e_step():
-            handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m, host=True)
+        api = "rtat_b200_dgemm_host (pinned host buffers)"
+        h2d = (ar * ac + br * bc) * esz
+        mg_mode = os.environ.get("RTAT_B200_MG_E2E", "")  # experiments: "percall" = every rank uploads all of A; "spin" = polling kernels
+        if mg_mode == "spin":
+            handle.set_option("mg.spin_wait", 1)
+        if os.environ.get("RTAT_B200_HOST_TRACE"):  # per-stage timeline of every host-entry call on stderr
+            handle.set_option("host.trace", 1)
+        if world > 1 and transport != "nccl-broadcast" and mg_mode != "percall":
+            # host-buffer column split: every rank uploads 1/world of each K-panel of A into its replica and pulls the other
+            # shares from the peers' replicas over NVLink (copy engines, flag-synchronised) — A crosses PCIe once per step
+            # release the device-resident A of the HBM-resident bench above: the host entry owns its own replicas
+            torch.cuda.synchronize()
+            if rank != 0:
+                cs.close_shared(A_src)
+            A = A_src = A_stage = None
+            dist.barrier()
+            if rank == 0:
+                cs.free_shared(a_ptr)
+            torch.cuda.empty_cache()
+            hbytes = cs.host_setup(ar * ac * esz)
+            mine = torch.tensor(list(hbytes), dtype=torch.uint8, device="cuda")
+            allh = torch.empty(rt.mg.HANDLE_BYTES * world, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine)
+            cs.host_connect(allh.cpu().numpy().tobytes())
+            api = ("rtat_b200_mg_dgemm_host (pinned host buffers): per K-panel every rank uploads its 1/N share of A and pulls the "
+                   "others over NVLink; B/C column blocks over the rank's own PCIe link")
+            h2d = (ar * ac + br * bc * world) * esz
+
+            def e2e_step():
+                cs.dgemm_host(ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m)
+        else:
+            h2d = (ar * ac + br * bc) * world * esz
+
+            def e2e_step():
+                handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m, host=True)
 
         e2e_step()
         torch.cuda.synchronize()
@@ -404,9 +437,8 @@ def main():
             t = torch.tensor([t1], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t1 = float(t.item())
-        h2d = (ar * ac + br * bc) * world * esz
         e2e = {"value": flops / (t1 * 1e-3) * 1e-12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": m * n * esz,
-               "ms_per_step": t1, "steps": e_steps, "api": "rtat_b200_dgemm_host (pinned host buffers)" + (f", one call per rank on its column block of C; A crosses each GPU's own PCIe link" if world > 1 else "")}
+               "ms_per_step": t1, "steps": e_steps, "api": api}
 
     if rank == 0:
         stats = planner.statistics() if world == 1 else [{"options": []}]

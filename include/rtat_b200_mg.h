@@ -53,6 +53,26 @@ int rtat_b200_mg_close_shared(rtat_b200_mg_t mg, void *peer_dptr);
 int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A_src,
                        int lda, double *A_stage, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc, int panels);
 
+/* ---- host-buffer column split: A, B_loc, C_loc in (pinned) host memory -----------------------------------------------
+ * The multi-GPU counterpart of rtat_b200_dgemm_host (rtat_b200.h).  Every rank passes the same full A and its own column
+ * block of op(B) / C.  A crosses PCIe ONCE per step in total: for every K-panel each rank uploads only its 1/world share
+ * into its replica of A, publishes a flag, and pulls the other shares from the peers' replicas over NVLink with the copy
+ * engines (replicas are IPC-mapped into every process).  Flags are 4-byte peer copies, waits are stream memory operations
+ * (cuStreamWaitValue32; a one-thread polling kernel with a 30 s timeout where the driver lacks them), so the exchange uses
+ * no SM and needs no process-group collective inside the step.  Around that exchange the schedule is the single-GPU host
+ * pipeline: K-panels of A against the leading column blocks while A is still arriving, then whole-K column blocks with
+ * their C blocks streaming back to the host.
+ *
+ * Setup (once): every rank calls _host_setup, the 64-byte handles are all-gathered through the caller's process group,
+ * every rank calls _host_connect with the world x 64 bytes in rank order.  _dgemm_host is collective: every rank must
+ * make the same sequence of calls (same m, k, transa, lda; n_loc > 0 on every rank).  It returns when C_loc has landed. */
+#define RTAT_B200_MG_MAX_WORLD 16
+int rtat_b200_mg_host_setup(rtat_b200_mg_t mg, size_t bytes_a, unsigned char handle_out[RTAT_B200_MG_HANDLE_BYTES]);
+int rtat_b200_mg_host_connect(rtat_b200_mg_t mg, const unsigned char *handles /* world x RTAT_B200_MG_HANDLE_BYTES */);
+int rtat_b200_mg_host_teardown(rtat_b200_mg_t mg);
+int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A,
+                            int lda, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc);
+
 #ifdef __cplusplus
 }
 #endif

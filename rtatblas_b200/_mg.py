@@ -24,6 +24,10 @@ def _mg_lib():
         L.rtat_b200_mg_close_shared.argtypes = [vp, vp]
         dp = C.POINTER(C.c_double)
         L.rtat_b200_mg_dgemm.argtypes = [vp, i, i, i, i, i, dp, vp, i, vp, vp, i, dp, vp, i, i]
+        L.rtat_b200_mg_host_setup.argtypes = [vp, sz, C.c_char_p]
+        L.rtat_b200_mg_host_connect.argtypes = [vp, C.c_char_p]
+        L.rtat_b200_mg_host_teardown.argtypes = [vp]
+        L.rtat_b200_mg_dgemm_host.argtypes = [vp, i, i, i, i, i, dp, vp, i, vp, i, dp, vp, i]
         _declared = True
     return L
 
@@ -83,3 +87,28 @@ class ColumnSplit:
         al, be = C.c_double(alpha), C.c_double(beta)
         _check(_mg_lib().rtat_b200_mg_dgemm(self._mg, transa, transb, m, n_loc, k, C.byref(al), _ptr(A_src), lda, _ptr(A_stage),
                                             _ptr(B_loc), ldb, C.byref(be), _ptr(C_loc), ldc, panels), "rtat_b200_mg_dgemm")
+
+    # ---- host-buffer column split (A, B_loc, C_loc in pinned host memory) ----
+    def host_setup(self, bytes_a):
+        """Allocate this rank's replica of A (+ flag page) and return its 64-byte IPC handle for the all-gather."""
+        buf = C.create_string_buffer(HANDLE_BYTES)
+        _check(_mg_lib().rtat_b200_mg_host_setup(self._mg, bytes_a, buf), "rtat_b200_mg_host_setup")
+        return buf.raw
+
+    def host_connect(self, handles):
+        """handles: world x 64 bytes in rank order (None when world == 1)."""
+        hb = None if handles is None else bytes(handles)
+        if hb is not None and len(hb) != HANDLE_BYTES * self.world:
+            raise RtatError("host_connect needs world x 64 handle bytes")
+        st = _mg_lib().rtat_b200_mg_host_connect(self._mg, hb)
+        if st != 0:
+            raise RtatError(f"rtat_b200_mg_host_connect failed ({st}): peer mapping unavailable")
+
+    def host_teardown(self):
+        _mg_lib().rtat_b200_mg_host_teardown(self._mg)
+
+    def dgemm_host(self, transa, transb, m, n_loc, k, alpha, A, lda, B_loc, ldb, beta, C_loc, ldc):
+        """Collective: every rank passes the full host A and its own column block of op(B) / C; returns when C_loc landed."""
+        al, be = C.c_double(alpha), C.c_double(beta)
+        _check(_mg_lib().rtat_b200_mg_dgemm_host(self._mg, transa, transb, m, n_loc, k, C.byref(al), _ptr(A), lda, _ptr(B_loc), ldb,
+                                                 C.byref(be), _ptr(C_loc), ldc), "rtat_b200_mg_dgemm_host")

@@ -1,6 +1,7 @@
 // C ABI entry points (include/rtat_b200.h): handle management, argument validation, dispatch.
 // Replaces the cuBLAS side of the reference's rtat::gpu:: alias table (src/gpu-api/gpu-api.h:87-113).
 #include "common.cuh"
+#include "host_pipeline.cuh"
 #include <cstring>
 #include <new>
 
@@ -306,7 +307,7 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t h, float *x, size_t n, uint64_t 
 
 }  // extern "C"
 
-// ---- host-buffer entry points ------------------------------------------------------------------
+// ---- host-buffer entry points (pipeline: host_pipeline.cuh) ---------------------------------------
 template <typename T, typename GemmFn>
 static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n, int k,
                      const T *alpha, const T *A, int lda, const T *B, int ldb, const T *beta, T *C,
@@ -317,147 +318,7 @@ static int gemm_host(rtat_b200_handle_t h, int transa, int transb, int m, int n,
   if (st) return st;
   if (m == 0 || n == 0) return RTAT_B200_STATUS_SUCCESS;
   if (!A || !B || !C) return RTAT_B200_STATUS_INVALID_VALUE;
-  size_t cols_a = transa == RTAT_B200_OP_N ? k : m, cols_b = transb == RTAT_B200_OP_N ? n : k;
-  auto round = [](size_t b) { return (b + 511) & ~size_t(511); };
-  size_t bytes_a = round(sizeof(T) * lda * cols_a), bytes_b = round(sizeof(T) * ldb * cols_b),
-         bytes_c = round(sizeof(T) * size_t(ldc) * n);
-  size_t need = bytes_a + bytes_b + bytes_c;
-  if (need > h->staging_bytes) {
-    cudaStreamSynchronize(h->stream);
-    if (h->staging) cudaFree(h->staging);
-    h->staging = nullptr;
-    h->staging_bytes = 0;
-    if (cudaMalloc(&h->staging, need) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return RTAT_B200_STATUS_ALLOC_FAILED;
-    }
-    h->staging_bytes = need;
-  }
-  char *base = static_cast<char *>(h->staging);
-  T *dA = reinterpret_cast<T *>(base), *dB = reinterpret_cast<T *>(base + bytes_a), *dC = reinterpret_cast<T *>(base + bytes_a + bytes_b);
-  auto cuda_ok = [](cudaError_t e, const char *what) {
-    if (e == cudaSuccess) return true;
-    fprintf(stderr, "rtat_b200 host entry: %s: %s\n", what, cudaGetErrorString(e));
-    (void)cudaGetLastError();
-    return false;
-  };
-  // Lazily created side streams / events: H2D, math and D2H run as a column-block pipeline.
-  if (!h->copy_in) {
-    if (!cuda_ok(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking), "stream") ||
-        !cuda_ok(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking), "stream"))
-      return RTAT_B200_STATUS_ALLOC_FAILED;
-    for (auto &e : h->host_events)
-      if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return RTAT_B200_STATUS_ALLOC_FAILED;
-  }
-  cudaStream_t s = h->stream, sin = h->copy_in, sout = h->copy_out;
-  constexpr int MAX_BLOCKS = 8, MAX_PANELS = 8;
-  // Column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128.
-  int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
-  nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
-  int blocks = (n + nb - 1) / nb;
-  int col0[MAX_BLOCKS + 2], cols[MAX_BLOCKS + 2];
-  for (int j = 0; j < blocks; j++) {
-    col0[j] = j * nb;
-    cols[j] = (col0[j] + nb > n) ? n - col0[j] : nb;
-  }
-  // the last block's copy back to the host is the one transfer nothing can hide: halve it
-  if (blocks > 1 && cols[blocks - 1] >= 512) {
-    const int half = cols[blocks - 1] / 2 / 128 * 128;
-    col0[blocks] = col0[blocks - 1] + half;
-    cols[blocks] = cols[blocks - 1] - half;
-    cols[blocks - 1] = half;
-    blocks++;
-  }
-  // Schedule.  Every column block needs all of A, so a plain column-block pipeline idles the GPU while A crosses
-  // PCIe.  Phase 1 therefore runs the first `lead` column blocks K-panel by K-panel: panel p of A and the matching
-  // pieces of those blocks are copied, then multiplied (beta, then 1) while panel p + 1 is in flight.  `lead` is
-  // chosen so that those blocks' math takes about as long as copying A plus their own share of B.  Phase 2 is the
-  // column-block pipeline for the rest (A is resident by then): copy B_j, multiply, copy C_j back.
-  int panels = 1, lead = 0;
-  if (blocks > 1 && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
-    panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
-    const double pcie = 50e9, rate = sizeof(T) == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
-    const double t_a = double(bytes_a) / pcie, t_b = double(sizeof(T)) * k * nb / pcie, t_mm = 2.0 * m * nb * double(k) / rate;
-    lead = t_mm > t_b ? int(t_a / (t_mm - t_b) + 0.5) : blocks;  // in units of nb columns: leading blocks are full
-    if (lead < 1) lead = 1;
-    // host.panels / host.lead: overrides for experiments (0 = the choice above)
-    if (opt(h, "host.panels") > 0) panels = opt(h, "host.panels") < MAX_PANELS ? opt(h, "host.panels") : MAX_PANELS;
-    if (opt(h, "host.lead") > 0) lead = opt(h, "host.lead");
-    if (lead > blocks) lead = blocks;
-  }
-  const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
-  // K-panel table; the first panel is split in two so that the math starts after half a panel of A has landed
-  int k0s[MAX_PANELS + 2], kcs[MAX_PANELS + 2], npanels = 0;
-  for (int p0 = 0; p0 < k; p0 += kp) {
-    k0s[npanels] = p0;
-    kcs[npanels++] = p0 + kp > k ? k - p0 : kp;
-  }
-  if (panels > 1 && kcs[0] >= 1024) {
-    for (int p = npanels; p > 1; p--) { k0s[p] = k0s[p - 1]; kcs[p] = kcs[p - 1]; }
-    const int half = kcs[0] / 2 / 16 * 16;
-    k0s[1] = half;
-    kcs[1] = kcs[0] - half;
-    kcs[0] = half;
-    npanels++;
-  }
-  cudaEvent_t *ev = h->host_events;
-  int next_event = 1;  // [0] is the entry fence
-  // everything queued on the H2D stream so far is visible to the math stream after this.  A failed record / wait would
-  // silently drop an ordering edge of the pipeline, so every one is checked.
-  auto landed = [&]() {
-    cudaEvent_t e = ev[next_event++];
-    return cuda_ok(cudaEventRecord(e, sin), "record H2D") && cuda_ok(cudaStreamWaitEvent(s, e, 0), "wait for H2D");
-  };
-  // stored element (row, col) of a column-major host/device pair -> 2-D copy of a rows x cols window
-  auto h2d_window = [&](T *dst, const T *src, int ld, size_t row0, size_t col0, size_t rows, size_t cols) {
-    const size_t off = col0 * ld + row0;
-    if (rows == (size_t)ld) return cudaMemcpyAsync(dst + off, src + off, sizeof(T) * rows * cols, cudaMemcpyHostToDevice, sin);
-    return cudaMemcpy2DAsync(dst + off, sizeof(T) * ld, src + off, sizeof(T) * ld, sizeof(T) * rows, cols, cudaMemcpyHostToDevice, sin);
-  };
-  auto d2h_block = [&](int j0, int cnt) {  // only the m x cnt window (ldc padding rows on the host are left untouched)
-    cudaEvent_t e = ev[next_event++];
-    return cuda_ok(cudaEventRecord(e, s), "record GEMM") && cuda_ok(cudaStreamWaitEvent(sout, e, 0), "wait for GEMM") &&
-           cuda_ok(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, sizeof(T) * ldc, dC + (size_t)j0 * ldc, sizeof(T) * ldc, sizeof(T) * m, cnt,
-                                     cudaMemcpyDeviceToHost, sout), "D2H C");
-  };
-  if (!cuda_ok(cudaEventRecord(ev[0], s), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-  if (!cuda_ok(cudaStreamWaitEvent(sin, ev[0], 0), "fence")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-
-  // ---- phase 1: K-panels of A against the first `lead` column blocks (panels == 1: all of A, no blocks) ----
-  for (int p = 0; p < npanels; p++) {
-    const int p0 = k0s[p], kc = kcs[p];
-    // A is stored m x k (N) or k x m (T): the panel is a column block or a row block
-    cudaError_t e = transa == RTAT_B200_OP_N ? h2d_window(dA, A, lda, 0, p0, m, kc) : h2d_window(dA, A, lda, p0, 0, kc, m);
-    if (!cuda_ok(e, "H2D A")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    for (int j = 0; j < lead; j++) {
-      const int j0 = col0[j], cnt = cols[j];
-      // op(B) block j, K-panel p: B is stored k x n (N) or n x k (T)
-      e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, p0, j0, kc, cnt) : h2d_window(dB, B, ldb, j0, p0, cnt, kc);
-      if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-      if (p == 0 && *beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-      if (!landed()) return RTAT_B200_STATUS_EXECUTION_FAILED;
-      const T *Ap = transa == RTAT_B200_OP_N ? dA + (size_t)p0 * lda : dA + p0;
-      const T *Bjp = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb + p0 : dB + (size_t)p0 * ldb + j0;
-      st = gemm_fn(h, transa, transb, m, cnt, kc, *alpha, Ap, lda, Bjp, ldb, p == 0 ? *beta : T(1), dC + (size_t)j0 * ldc, ldc);
-      if (st) return st;
-      if (p0 + kc >= k && !d2h_block(j0, cnt)) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    }
-  }
-  // ---- phase 2: whole-K column blocks ----
-  for (int j = lead; j < blocks; j++) {
-    const int j0 = col0[j], cnt = cols[j];
-    cudaError_t e = transb == RTAT_B200_OP_N ? h2d_window(dB, B, ldb, 0, j0, k, cnt) : h2d_window(dB, B, ldb, j0, 0, cnt, k);
-    if (!cuda_ok(e, "H2D B")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    if (*beta != T(0) && !cuda_ok(h2d_window(dC, C, ldc, 0, j0, m, cnt), "H2D C")) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    if (!landed()) return RTAT_B200_STATUS_EXECUTION_FAILED;
-    const T *Bj = transb == RTAT_B200_OP_N ? dB + (size_t)j0 * ldb : dB + j0;
-    st = gemm_fn(h, transa, transb, m, cnt, k, *alpha, dA, lda, Bj, ldb, *beta, dC + (size_t)j0 * ldc, ldc);
-    if (st) return st;
-    if (!d2h_block(j0, cnt)) return RTAT_B200_STATUS_EXECUTION_FAILED;
-  }
-  if (!cuda_ok(cudaStreamSynchronize(sout), "synchronize") || !cuda_ok(cudaStreamSynchronize(s), "synchronize"))
-    return RTAT_B200_STATUS_EXECUTION_FAILED;
-  return RTAT_B200_STATUS_SUCCESS;
+  return gemm_host_pipeline<T>(h, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, gemm_fn, nullptr);
 }
 
 extern "C" {

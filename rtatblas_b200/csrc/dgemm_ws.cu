@@ -47,6 +47,8 @@ struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLOT_DOUBLES = CONSUMER_WARPS * 32 * (WM / 8) * (WN / 8) * 2;
   static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // consumers of a ragged tile skip single DMMA blocks (64x64 tiles) or only whole warps (128x128: at the register cap)
+  static constexpr bool FINE_EDGES = BM_ == 64;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
 using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
@@ -71,6 +73,12 @@ struct Params {
   // SYRK (TRI kernels): 1 = only the lower triangle of C is computed and written, 2 = upper.  Tiles are
   // then the tiles_m (tiles_m + 1) / 2 tiles that touch the triangle, numbered row by row.
   int tri;
+  // Tile order (GEMM): the tm_full x tn_full full tiles first (grouped raster), then the ragged last column of tiles,
+  // then the ragged last row, then the corner.  The consumers of a partial tile skip the DMMA blocks that lie wholly
+  // outside C, so those tiles are cheap; last in the order they shorten the tail instead of opening a hole in a wave.
+  // (Charging them less in the stream-K split — CTAs given equal weighted lengths — measured 5-20 % slower on config 3
+  // than equal k-tile counts: the ring protocol and operand delivery of a partial tile cost what a full one's do.)
+  int tm_full, tn_full, n_int, e_col, e_row;
 };
 
 // Tile t of a triangular enumeration -> (i, j) with i >= j: t = i (i + 1) / 2 + j.
@@ -303,10 +311,18 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       n0 = (p.tri == 1 ? j : i) * BN;
       return;
     }
+    if (tile >= p.n_int) {  // ragged edge tiles, after all full ones
+      tile -= p.n_int;
+      if (tile < p.e_col) { m0 = tile * BM; n0 = p.tn_full * BN; return; }
+      tile -= p.e_col;
+      m0 = p.tm_full * BM;
+      n0 = (tile < p.e_row ? tile : p.tn_full) * BN;
+      return;
+    }
     constexpr int GROUP = 8;
-    int group_size = GROUP * p.tiles_n;
+    int group_size = GROUP * p.tn_full;
     int first_m = (tile / group_size) * GROUP;
-    int gm = min(p.tiles_m - first_m, GROUP);
+    int gm = min(p.tm_full - first_m, GROUP);
     m0 = (first_m + (tile % group_size) % gm) * BM;
     n0 = ((tile % group_size) / gm) * BN;
   };
@@ -391,31 +407,70 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = seg.kb; kt < seg.ke; kt++) {
-      mbar_wait(bar_base + 8 * stage, phase);
-      const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-      double fa[2][MI], fb[2][NI];
+    // DMMA blocks of this warp that touch C: a ragged tile's consumers skip the rest (blocks are 8 rows / columns of a
+    // K-contiguous operand, pairs of blocks interleave within 16 of an M/N-contiguous one)
+    const int rv = min(max(p.m - m0 - wm0, 0), WM), cv = min(max(p.n - n0 - wn0, 0), WN);
+    const int mi_act = KCA ? (rv + 7) / 8 : 2 * ((rv + 15) / 16), ni_act = KCB ? (cv + 7) / 8 : 2 * ((cv + 15) / 16);
+    const bool whole = mi_act == MI && ni_act == NI;
+    if (whole || !Cfg::FINE_EDGES) {
+      // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
+      const bool active = whole || (mi_act > 0 && ni_act > 0);
+      for (int kt = seg.kb; kt < seg.ke; kt++) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (active) {
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          double fa[2][MI], fb[2][NI];
 #pragma unroll
-      for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa_addr.addr(i, 0));
+          for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa_addr.addr(i, 0));
 #pragma unroll
-      for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb_addr.addr(j, 0));
+          for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb_addr.addr(j, 0));
 #pragma unroll
-      for (int ks = 0; ks < KS; ks++) {
-        const int cur = ks & 1, nxt = cur ^ 1;
-        if (ks + 1 < KS) {
+          for (int ks = 0; ks < KS; ks++) {
+            const int cur = ks & 1, nxt = cur ^ 1;
+            if (ks + 1 < KS) {
 #pragma unroll
-          for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa_addr.addr(i, ks + 1));
+              for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa_addr.addr(i, ks + 1));
 #pragma unroll
-          for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb_addr.addr(j, ks + 1));
+              for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb_addr.addr(j, ks + 1));
+            }
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+#pragma unroll
+              for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[cur][i], fb[cur][j]);
+          }
         }
-#pragma unroll
-        for (int i = 0; i < MI; i++)
-#pragma unroll
-          for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[cur][i], fb[cur][j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    } else {
+      // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
+      for (int kt = seg.kb; kt < seg.ke; kt++) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+        if (mi_act > 0 && ni_act > 0) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            double fa[MI], fb[NI];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+              if (i < mi_act) fa[i] = lds64(sbase + fa_addr.addr(i, ks));
+#pragma unroll
+            for (int j = 0; j < NI; j++)
+              if (j < ni_act) fb[j] = lds64(sbase + fb_addr.addr(j, ks));
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+              if (i < mi_act) {
+#pragma unroll
+                for (int j = 0; j < NI; j++)
+                  if (j < ni_act) dmma(acc[i][j], fa[i], fb[j]);
+              }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
 
     if (seg.kb > 0) {
@@ -564,6 +619,32 @@ static int resident_ctas_per_sm(bool ta, bool tb, bool tma, bool tri) {
 #undef RTAT_OCC
 }
 
+// Cost of one k-tile of a tile with `rows` x `cols` valid elements (0 = the full extent), in sixteenths of a full tile's:
+// the DMMA blocks of the busiest SM sub-partition.  Warp w sits on sub-partition w % 4, owns M-slice w % (BM / WM) and
+// N-slice w / (BM / WM); a warp multiplies only the 8-row / 8-column blocks that touch C (pairs of blocks for an
+// M/N-contiguous operand).  Floor of 3/16: operand delivery and the ring protocol do not shrink with the tile.
+template <class Cfg>
+static int tile_cost(bool a_mn_contiguous, int rows, int cols) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN;
+  if (rows <= 0) rows = BM;
+  if (cols <= 0) cols = BN;
+  int load[4] = {0, 0, 0, 0};
+  for (int w = 0; w < Cfg::CONSUMER_WARPS; w++) {
+    int rv = rows - (w % (BM / WM)) * WM, cv = cols - (w / (BM / WM)) * WN;
+    rv = rv < 0 ? 0 : (rv > WM ? WM : rv);
+    cv = cv < 0 ? 0 : (cv > WN ? WN : cv);
+    // op(A) is M-contiguous when A is not transposed; op(B) N-contiguous when B is transposed.  Rounding pairs of blocks
+    // for both operands is the conservative choice for B.
+    int mi = a_mn_contiguous ? 2 * ((rv + 15) / 16) : (rv + 7) / 8, ni = 2 * ((cv + 15) / 16);
+    if (!Cfg::FINE_EDGES && mi > 0 && ni > 0) { mi = WM / 8; ni = WN / 8; }
+    load[w % 4] += mi * ni;
+  }
+  int worst = 0, full = (WM / 8) * (WN / 8) * (Cfg::CONSUMER_WARPS > 4 ? Cfg::CONSUMER_WARPS / 4 : 1);
+  for (int x : load) worst = x > worst ? x : worst;
+  int c = (16 * worst + full - 1) / full;
+  return c < 3 ? 3 : (c > 16 ? 16 : c);
+}
+
 template <class Cfg>
 static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B,
                    int ldb, double beta, double *C, int ldc, bool allow_tma, const char *tile_name, int tri) {
@@ -604,6 +685,15 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   if (!sk_tiles && p.num_tiles < grid) grid = p.num_tiles;
   p.dp_tiles = p.num_tiles - sk_tiles;
   p.sk_units = (long long)sk_tiles * p.kt;
+  // tile order and the cost of the ragged tiles (see Params)
+  if (tri) {
+    p.tm_full = p.tiles_m; p.tn_full = p.tiles_n; p.n_int = p.num_tiles; p.e_col = p.e_row = 0;
+  } else {
+    p.tm_full = m / BM; p.tn_full = n / BN;
+    p.n_int = p.tm_full * p.tn_full;
+    p.e_col = (n % BN) ? p.tm_full : 0;
+    p.e_row = (m % BM) ? p.tn_full : 0;
+  }
   if (sk_tiles) {
     // sized for the largest grid of either tile configuration up front, so no call ever pays a
     // reallocation (and its sync) later
@@ -655,9 +745,17 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
     // Estimated cost = padded tile area x waves.  128x128 tiles are the more efficient steady state
     // (98 % vs ~94 % of the DMMA pipe), 64x64 tiles waste less on ragged edges and keep stream-K fix-ups
     // four times smaller, which decides small problems.
+    // ragged tiles are charged what their busiest sub-partition multiplies (tile_cost)
     auto padded = [&](int bm) {
       double tm = (m + bm - 1) / bm, tn = (n + bm - 1) / bm;
-      return (tri ? tm * (tm + 1) / 2 : tm * tn) * bm * bm;
+      if (tri) return tm * (tm + 1) / 2 * bm * bm;
+      const bool amn = !ta;
+      auto cost = [&](int rows, int cols) { return bm == 128 ? tile_cost<ws::Cfg128>(amn, rows, cols) : tile_cost<ws::Cfg64>(amn, rows, cols); };
+      double tmf = m / bm, tnf = n / bm, sixteenths = 16.0 * tmf * tnf;
+      if (n % bm) sixteenths += tmf * cost(0, n % bm);
+      if (m % bm) sixteenths += tnf * cost(m % bm, 0);
+      if (m % bm && n % bm) sixteenths += cost(m % bm, n % bm);
+      return sixteenths / 16.0 * bm * bm;
     };
     // measured steady-state efficiencies: TMA producers 0.98 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
     const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);

@@ -1,7 +1,12 @@
 // Column-split multi-GPU DGEMM (include/rtat_b200_mg.h): K-panel pipeline of peer copies and DMMA GEMMs.
 #include <vector>
 #include "common.cuh"
+#include "host_pipeline.cuh"
 #include "../../include/rtat_b200_mg.h"
+
+using rtat_b200::HostPipelineHooks;
+using rtat_b200::host_cuda_ok;
+using rtat_b200::opt;
 
 struct rtat_b200_mg_context {
   rtat_b200_context *h = nullptr;
@@ -10,7 +15,60 @@ struct rtat_b200_mg_context {
   std::vector<cudaEvent_t> landed;    // panel p has arrived in A_stage
   std::vector<cudaEvent_t> consumed;  // panel p of the previous call has been read by its GEMM
   bool consumed_valid = false;
+  // ---- host-buffer entry (rtat_b200_mg_dgemm_host): every rank owns a replica of A in IPC-exportable memory, preceded by
+  // a flag page that the peers write into
+  char *replica = nullptr;                       // own allocation: [flag page][A]
+  size_t replica_bytes = 0;                      // bytes of A it can hold
+  char *peer[RTAT_B200_MG_MAX_WORLD] = {};       // the other ranks' allocations mapped here (own entry = replica)
+  cudaStream_t pull_stream = nullptr;            // peer pulls (copy engines) and the flag waits in front of them
+  cudaEvent_t pulled = nullptr;
+  unsigned generation = 0;                       // call counter: flags carry it, so they never need clearing
+  unsigned *generation_pinned = nullptr;         // pinned host word the generation is uploaded from
 };
+
+// Flag page layout (u32 words).  arrived[q][p]: rank q's share of K-panel p of call `generation` is in q's replica.
+// done[q]: rank q has finished reading this rank's replica for call `generation`.  status: a wait timed out.
+namespace {
+constexpr size_t FLAG_PAGE_BYTES = 8192;
+constexpr int MAX_PANEL_FLAGS = 64;
+__host__ __device__ inline size_t arrived_word(int q, int p) { return size_t(q) * MAX_PANEL_FLAGS + p; }
+__host__ __device__ inline size_t done_word(int q) { return 1024 + q; }
+constexpr size_t STATUS_WORD = 1024 + 64;
+constexpr size_t GEN_WORD = 1024 + 65;  // this rank's current generation, the source of the 4-byte flag copies
+
+// one thread: spin until *flag >= value (wrap-safe); gives up after 30 s and raises *status instead of hanging the GPU.
+// Fallback for drivers without stream memory operations (see wait_flag).
+__global__ void mg_wait_kernel(const unsigned *flag, unsigned value, unsigned *status) {
+  unsigned long long t0, now;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - value) >= 0) return;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+    if (now - t0 > 30000000000ull) {
+      atomicExch(status, 1u);
+      return;
+    }
+    __nanosleep(500);
+  }
+}
+
+// cuStreamWaitValue32 through the runtime (the library has no link-time dependency on libcuda)
+typedef int (*stream_wait_value32_fn)(cudaStream_t, unsigned long long addr, unsigned value, unsigned flags);
+stream_wait_value32_fn stream_wait_value32() {
+  static stream_wait_value32_fn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<stream_wait_value32_fn>(p);
+  }();
+  return fn;
+}
+}  // namespace
 
 static void ensure_events(rtat_b200_mg_context *mg, int panels) {
   while ((int)mg->landed.size() < panels) {
@@ -82,6 +140,7 @@ int rtat_b200_mg_destroy(rtat_b200_mg_t mg) {
   for (auto e : mg->landed) cudaEventDestroy(e);
   for (auto e : mg->consumed) cudaEventDestroy(e);
   cudaStreamDestroy(mg->copy_stream);
+  rtat_b200_mg_host_teardown(mg);
   delete mg;
   return RTAT_B200_STATUS_SUCCESS;
 }
@@ -185,6 +244,207 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
   }
   mg->consumed_valid = true;
   return RTAT_B200_STATUS_SUCCESS;
+}
+
+
+// ---- host-buffer column split ------------------------------------------------------------------------------------
+int rtat_b200_mg_host_setup(rtat_b200_mg_t mg, size_t bytes_a, unsigned char handle_out[RTAT_B200_MG_HANDLE_BYTES]) {
+  if (!mg || !handle_out || mg->world > RTAT_B200_MG_MAX_WORLD) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (mg->replica) return RTAT_B200_STATUS_INVALID_VALUE;  // one setup per context
+  void *p = nullptr;
+  if (cudaMalloc(&p, FLAG_PAGE_BYTES + bytes_a) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  if (cudaMemset(p, 0, FLAG_PAGE_BYTES) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(p);
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  }
+  cudaIpcMemHandle_t hnd;
+  if (cudaIpcGetMemHandle(&hnd, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p);
+    return RTAT_B200_STATUS_NOT_SUPPORTED;
+  }
+  memcpy(handle_out, &hnd, sizeof hnd);
+  if (cudaStreamCreateWithFlags(&mg->pull_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&mg->pulled, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p);
+    return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  if (cudaMallocHost(&mg->generation_pinned, 64) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p);
+    return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  mg->replica = static_cast<char *>(p);
+  mg->replica_bytes = bytes_a;
+  mg->peer[mg->rank] = mg->replica;
+  mg->generation = 0;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_mg_host_connect(rtat_b200_mg_t mg, const unsigned char *handles) {
+  if (!mg || !mg->replica || (mg->world > 1 && !handles)) return RTAT_B200_STATUS_INVALID_VALUE;
+  for (int q = 0; q < mg->world; q++) {
+    if (q == mg->rank || mg->peer[q]) continue;
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handles + (size_t)q * RTAT_B200_MG_HANDLE_BYTES, sizeof hnd);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      fprintf(stderr, "rtat_b200_mg: cudaIpcOpenMemHandle(rank %d) failed: %s\n", q, cudaGetErrorString(cudaGetLastError()));
+      return RTAT_B200_STATUS_NOT_SUPPORTED;
+    }
+    mg->peer[q] = static_cast<char *>(p);
+  }
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_mg_host_teardown(rtat_b200_mg_t mg) {
+  if (!mg) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  if (!mg->replica) return RTAT_B200_STATUS_SUCCESS;
+  cudaDeviceSynchronize();
+  for (int q = 0; q < mg->world; q++)
+    if (q != mg->rank && mg->peer[q]) cudaIpcCloseMemHandle(mg->peer[q]);
+  for (auto &p : mg->peer) p = nullptr;
+  cudaFree(mg->replica);
+  mg->replica = nullptr;
+  if (mg->pulled) cudaEventDestroy(mg->pulled);
+  if (mg->pull_stream) cudaStreamDestroy(mg->pull_stream);
+  if (mg->generation_pinned) cudaFreeHost(mg->generation_pinned);
+  mg->generation_pinned = nullptr;
+  mg->pulled = nullptr;
+  mg->pull_stream = nullptr;
+  return RTAT_B200_STATUS_SUCCESS;
+}
+
+int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, int n_loc, int k, const double *alpha, const double *A,
+                            int lda, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc) {
+  if (!mg || !alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
+  if ((transa != RTAT_B200_OP_N && transa != RTAT_B200_OP_T) || (transb != RTAT_B200_OP_N && transb != RTAT_B200_OP_T) || m < 0 ||
+      n_loc < 0 || k < 0)
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
+  const int rows_a = ta ? k : m, rows_b = tb ? n_loc : k;
+  if (lda < (rows_a > 1 ? rows_a : 1) || ldb < (rows_b > 1 ? rows_b : 1) || ldc < (m > 1 ? m : 1)) return RTAT_B200_STATUS_INVALID_VALUE;
+  if (!mg->replica) return RTAT_B200_STATUS_NOT_INITIALIZED;
+  const size_t cols_a = ta ? m : k;
+  if (sizeof(double) * lda * cols_a > mg->replica_bytes) return RTAT_B200_STATUS_INVALID_VALUE;
+  for (int q = 0; q < mg->world; q++)
+    if (!mg->peer[q]) return RTAT_B200_STATUS_NOT_INITIALIZED;  // host_connect has not run
+  if (m == 0) return RTAT_B200_STATUS_SUCCESS;  // the same on every rank: nobody signals, nobody waits
+  // every rank carries its share of A even if its own column block were empty; keep the contract simple instead
+  if (n_loc == 0 || !A || !B_loc || !C_loc) return RTAT_B200_STATUS_INVALID_VALUE;
+  rtat_b200_context *h = mg->h;
+  const int R = mg->rank, W = mg->world;
+  // The call is collective (every rank makes it, the same number of times): the flags carry the call's generation number,
+  // so they never need clearing and a stale value can never satisfy a wait.
+  const unsigned gen = ++mg->generation;
+  double *dA = reinterpret_cast<double *>(mg->replica + FLAG_PAGE_BYTES);
+  unsigned *my_flags = reinterpret_cast<unsigned *>(mg->replica);
+  const bool spin = opt(h, "mg.spin_wait") != 0 || !stream_wait_value32();
+  // wait on `stream` until *flag >= value: a stream memory operation (no SM involved), else a one-thread polling kernel
+  auto wait_flag = [&](cudaStream_t stream, unsigned *flag, unsigned value) {
+    if (!spin) {
+      int rc = stream_wait_value32()(stream, (unsigned long long)(uintptr_t)flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+      if (rc == 0) return true;
+      fprintf(stderr, "rtat_b200_mg: cuStreamWaitValue32 failed (%d)\n", rc);
+      return false;
+    }
+    mg_wait_kernel<<<1, 1, 0, stream>>>(flag, value, my_flags + STATUS_WORD);
+    return host_cuda_ok(cudaPeekAtLastError(), "flag wait kernel");
+  };
+  // publish `gen` into word `word` of every peer's flag page, in `stream` order, with the copy engines: a 4-byte peer copy
+  // of this rank's generation word.  No kernel: a spinning waiter elsewhere can never hold it up.
+  auto signal_peers = [&](cudaStream_t stream, size_t word) {
+    for (int q = 0; q < W; q++) {
+      if (q == R) continue;
+      if (!host_cuda_ok(cudaMemcpyAsync(reinterpret_cast<unsigned *>(mg->peer[q]) + word, my_flags + GEN_WORD, sizeof(unsigned),
+                                        cudaMemcpyDeviceToDevice, stream), "flag write"))
+        return false;
+    }
+    return true;
+  };
+  int panel = 0;
+  bool started = false;
+  HostPipelineHooks<double> hooks;
+  hooks.dA = dA;
+  hooks.a_share = 1.0 / W;
+  hooks.pcie_rate = W > 3 ? 150e9 / W : 50e9;  // the host side of one box sustains about 150 GB/s over all links
+  hooks.fetch_a = [&](size_t row0, size_t col0, size_t rows, size_t cols) {
+    cudaStream_t sin = h->copy_in, spull = mg->pull_stream;
+    const int p = panel++;
+    if (p >= MAX_PANEL_FLAGS) return false;
+    if (!started && W > 1) {
+      started = true;
+      // this call's generation number, where the copy engines can read it from
+      if (!host_cuda_ok(cudaMemcpyAsync(my_flags + GEN_WORD, &mg->generation_pinned[0], sizeof(unsigned), cudaMemcpyHostToDevice, sin),
+                        "generation word"))
+        return false;
+      // this rank's replica is about to be overwritten: every peer must have finished reading last call's contents
+      if (gen > 1)
+        for (int q = 0; q < W; q++)
+          if (q != R && !wait_flag(sin, my_flags + done_word(q), gen - 1)) return false;
+    }
+    auto window = [&](int q, size_t &c0, size_t &cn) {
+      int f, c;
+      rtat_b200_mg_partition((int)cols, W, q, &f, &c);
+      c0 = col0 + f;
+      cn = c;
+    };
+    size_t c0, cn;
+    window(R, c0, cn);
+    if (cn > 0) {
+      const size_t off = c0 * lda + row0;
+      cudaError_t e = rows == (size_t)lda
+                          ? cudaMemcpyAsync(dA + off, A + off, sizeof(double) * rows * cn, cudaMemcpyHostToDevice, sin)
+                          : cudaMemcpy2DAsync(dA + off, sizeof(double) * lda, A + off, sizeof(double) * lda, sizeof(double) * rows, cn,
+                                              cudaMemcpyHostToDevice, sin);
+      if (!host_cuda_ok(e, "H2D share of A")) return false;
+    }
+    if (W > 1) {
+      if (!signal_peers(sin, arrived_word(R, p))) return false;
+      for (int i = 1; i < W; i++) {
+        const int q = (R + i) % W;  // every rank starts with a different peer
+        window(q, c0, cn);
+        if (!wait_flag(spull, my_flags + arrived_word(q, p), gen)) return false;
+        if (cn == 0) continue;
+        const size_t off = c0 * lda + row0;
+        const double *src = reinterpret_cast<const double *>(mg->peer[q] + FLAG_PAGE_BYTES) + off;
+        if (!host_cuda_ok(cudaMemcpy2DAsync(dA + off, sizeof(double) * lda, src, sizeof(double) * lda, sizeof(double) * rows, cn,
+                                            cudaMemcpyDeviceToDevice, spull), "peer pull of A"))
+          return false;
+      }
+    }
+    return true;
+  };
+  hooks.fence_a = [&](cudaStream_t s) {
+    if (W == 1) return true;
+    return host_cuda_ok(cudaEventRecord(mg->pulled, mg->pull_stream), "record pulls") &&
+           host_cuda_ok(cudaStreamWaitEvent(s, mg->pulled, 0), "wait for pulls");
+  };
+  mg->generation_pinned[0] = gen;
+  auto gemm_fn = [](rtat_b200_context *hh, int ta_, int tb_, int mm, int nn, int kk, double al, const double *a, int la, const double *b,
+                    int lb, double be, double *c, int lc) { return rtat_b200::dgemm(hh, ta_, tb_, mm, nn, kk, al, a, la, b, lb, be, c, lc); };
+  int st = rtat_b200::gemm_host_pipeline<double>(h, transa, transb, m, n_loc, k, alpha, A, lda, B_loc, ldb, beta, C_loc, ldc, gemm_fn, &hooks);
+  if (W > 1) {
+    if (!started && !host_cuda_ok(cudaMemcpyAsync(my_flags + GEN_WORD, &mg->generation_pinned[0], sizeof(unsigned), cudaMemcpyHostToDevice,
+                                                  mg->pull_stream), "generation word"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    // tell every peer that this rank no longer reads their replicas of this generation (all pulls are behind us on pull_stream)
+    if (!signal_peers(mg->pull_stream, done_word(R))) return RTAT_B200_STATUS_EXECUTION_FAILED;
+    unsigned status = 0;
+    if (!host_cuda_ok(cudaStreamSynchronize(mg->pull_stream), "synchronize pulls") ||
+        !host_cuda_ok(cudaStreamSynchronize(h->copy_in), "synchronize H2D") ||
+        !host_cuda_ok(cudaMemcpy(&status, my_flags + STATUS_WORD, sizeof status, cudaMemcpyDeviceToHost), "read status"))
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    if (status) {
+      fprintf(stderr, "rtat_b200_mg: rank %d timed out waiting for a peer's share of A (is every rank making this call?)\n", R);
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    }
+  }
+  return st;
 }
 
 }  // extern "C"

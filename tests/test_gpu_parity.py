@@ -478,3 +478,22 @@ def test_mg_panel_pipeline_on_one_gpu(oracle, handle):
         cs.dgemm(ta, tb, m, n, k, 1.25, dA, lda, None, dB, br, -0.5, dC, m)
         assert np.all(np.abs(view(host(dC), m, n, m) - ex) <= gemm_tolerance(np.float64, k, ab, ex))
         cs.close()
+
+
+def test_multi_gpu_host_entry_single_rank_and_all_visible_gpus():
+    """rtat_b200_mg_dgemm_host: world 1 in-process path, then one rank per visible GPU (when the box has more than one)
+    under torch.distributed.run; tests/mg_host_worker.py holds the checks."""
+    import os
+    import subprocess
+    import sys
+
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mg_host_worker.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    res = subprocess.run([sys.executable, worker], capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "mg_host ok rank 0/1" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    ngpu = torch.cuda.device_count()
+    if ngpu >= 2:
+        n = 2 if ngpu < 4 else 4
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                              "--master-port", "29577", worker], capture_output=True, text=True, timeout=900, env=env)
+        assert res.returncode == 0 and res.stdout.count("mg_host ok") == n, res.stdout[-2000:] + res.stderr[-4000:]

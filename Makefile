@@ -14,7 +14,7 @@ KERNEL_OBJS := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(KERNEL_SRCS))
 
 all: $(LIBDIR)/librtat_b200.so host oracle
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/rtat_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 

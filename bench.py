@@ -390,7 +390,10 @@ def main():
 
         api = "rtat_b200_dgemm_host (pinned host buffers)"
         h2d = (ar * ac + br * bc) * esz
-        mg_mode = os.environ.get("RTAT_B200_MG_E2E", "")  # experiments: "percall" = every rank uploads all of A; "spin" = polling kernels
+        # experiments: "percall" = every rank uploads all of A; "push" = flags pushed to the peers (stream memops wait); "spin" = push + polling kernels
+        mg_mode = os.environ.get("RTAT_B200_MG_E2E", "")
+        if mg_mode in ("push", "spin"):
+            handle.set_option("mg.signal", 0)
         if mg_mode == "spin":
             handle.set_option("mg.spin_wait", 1)
         if os.environ.get("RTAT_B200_HOST_TRACE"):  # per-stage timeline of every host-entry call on stderr

@@ -21,6 +21,8 @@ struct HostPipelineHooks {
   std::function<bool(size_t row0, size_t col0, size_t rows, size_t cols)> fetch_a;
   // Make `s` wait for whatever fetch_a queued outside `sin` (peer pulls).  Null: nothing.
   std::function<bool(cudaStream_t s)> fence_a;
+  // set by the pipeline when host.trace is on: timestamp `stream` under a label (what, panel, index)
+  std::function<void(cudaStream_t stream, const char *what, int a, int b)> mark;
   T *dA = nullptr;          // device home of A (null: the handle's staging)
   double a_share = 1.0;     // fraction of A that crosses this GPU's PCIe link
   double pcie_rate = 50e9;  // bytes/s this GPU's link can expect (only the split point of the schedule depends on it)
@@ -37,7 +39,7 @@ inline bool host_cuda_ok(cudaError_t e, const char *what) {
 // device GEMM (value alpha / beta).  Returns after C has landed in host memory.
 template <typename T, typename GemmFn>
 int gemm_host_pipeline(rtat_b200_context *h, int transa, int transb, int m, int n, int k, const T *alpha, const T *A, int lda,
-                       const T *B, int ldb, const T *beta, T *C, int ldc, GemmFn gemm_fn, const HostPipelineHooks<T> *hooks) {
+                       const T *B, int ldb, const T *beta, T *C, int ldc, GemmFn gemm_fn, HostPipelineHooks<T> *hooks) {
   auto cuda_ok = host_cuda_ok;
   size_t cols_a = transa == RTAT_B200_OP_N ? k : m, cols_b = transb == RTAT_B200_OP_N ? n : k;
   auto round = [](size_t b) { return (b + 511) & ~size_t(511); };
@@ -135,6 +137,7 @@ int gemm_host_pipeline(rtat_b200_context *h, int transa, int transb, int m, int 
     marks.emplace_back(buf, e);
   };
   mark(s, "start", 0, 0);
+  if (hooks && trace) hooks->mark = mark;
   // everything queued on the H2D stream so far is visible to the math stream after this.  A failed record / wait would
   // silently drop an ordering edge of the pipeline, so every one is checked.
   auto landed = [&]() {
@@ -206,11 +209,15 @@ int gemm_host_pipeline(rtat_b200_context *h, int transa, int transb, int m, int 
   if (trace) {
     cudaDeviceSynchronize();
     fprintf(stderr, "rtat_b200 host pipeline: m %d n %d k %d, %d K-panels, %d column blocks, %d leading\n", m, n, k, npanels, blocks, lead);
+    std::string out;
     for (auto &mk : marks) {
       float ms = 0;
       cudaEventElapsedTime(&ms, marks[0].second, mk.second);
-      fprintf(stderr, "  %9.3f ms  %s\n", ms, mk.first.c_str());
+      char line[128];
+      snprintf(line, sizeof line, "  dev%d %9.3f ms  %s\n", h->device, ms, mk.first.c_str());
+      out += line;
     }
+    fputs(out.c_str(), stderr);
     for (auto &mk : marks) cudaEventDestroy(mk.second);
   }
   return RTAT_B200_STATUS_SUCCESS;

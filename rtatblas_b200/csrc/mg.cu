@@ -22,6 +22,7 @@ struct rtat_b200_mg_context {
   char *peer[RTAT_B200_MG_MAX_WORLD] = {};       // the other ranks' allocations mapped here (own entry = replica)
   cudaStream_t pull_stream = nullptr;            // peer pulls (copy engines) and the flag waits in front of them
   cudaEvent_t pulled = nullptr;
+  int signal_mode = 1;                           // flag transport (mg.signal), fixed by _host_setup: who writes which page
   unsigned generation = 0;                       // call counter: flags carry it, so they never need clearing
   unsigned *generation_pinned = nullptr;         // pinned host word the generation is uploaded from
 };
@@ -282,6 +283,7 @@ int rtat_b200_mg_host_setup(rtat_b200_mg_t mg, size_t bytes_a, unsigned char han
   mg->replica_bytes = bytes_a;
   mg->peer[mg->rank] = mg->replica;
   mg->generation = 0;
+  mg->signal_mode = opt(mg->h, "mg.signal", 1);
   return RTAT_B200_STATUS_SUCCESS;
 }
 
@@ -343,10 +345,19 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
   const unsigned gen = ++mg->generation;
   double *dA = reinterpret_cast<double *>(mg->replica + FLAG_PAGE_BYTES);
   unsigned *my_flags = reinterpret_cast<unsigned *>(mg->replica);
+  // How a flag travels (mg.signal):
+  //   1 (default) — the writer sets the word in its OWN page with a 4-byte H2D copy on the stream that carried the data (same
+  //       copy engine as the upload, so strictly behind it), and a reader polls the writer's page over NVLink with a one-thread
+  //       kernel.  Every cross-GPU access is a read by the side that needs the data; nothing is pushed.
+  //   0 — the writer pushes the word into every peer's page with 4-byte peer copies and a reader waits on its own page with a
+  //       stream memory operation (cuStreamWaitValue32; mg.spin_wait = 1: the polling kernel).  Measured on 2 GPUs: the pushed
+  //       words land only when the writer's upload stream has drained (~150 ms late), which serialises the whole exchange.
+  const int signal_mode = mg->signal_mode;
   const bool spin = opt(h, "mg.spin_wait") != 0 || !stream_wait_value32();
-  // wait on `stream` until *flag >= value: a stream memory operation (no SM involved), else a one-thread polling kernel
-  auto wait_flag = [&](cudaStream_t stream, unsigned *flag, unsigned value) {
-    if (!spin) {
+  // wait on `stream` until word `word` written by rank q reaches `value`
+  auto wait_flag = [&](cudaStream_t stream, int q, size_t word, unsigned value) {
+    unsigned *flag = (signal_mode == 1 ? reinterpret_cast<unsigned *>(mg->peer[q]) : my_flags) + word;
+    if (signal_mode != 1 && !spin) {
       int rc = stream_wait_value32()(stream, (unsigned long long)(uintptr_t)flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
       if (rc == 0) return true;
       fprintf(stderr, "rtat_b200_mg: cuStreamWaitValue32 failed (%d)\n", rc);
@@ -355,9 +366,11 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
     mg_wait_kernel<<<1, 1, 0, stream>>>(flag, value, my_flags + STATUS_WORD);
     return host_cuda_ok(cudaPeekAtLastError(), "flag wait kernel");
   };
-  // publish `gen` into word `word` of every peer's flag page, in `stream` order, with the copy engines: a 4-byte peer copy
-  // of this rank's generation word.  No kernel: a spinning waiter elsewhere can never hold it up.
+  // publish `gen` as word `word` (one of this rank's words) in `stream` order
   auto signal_peers = [&](cudaStream_t stream, size_t word) {
+    if (signal_mode == 1)
+      return host_cuda_ok(cudaMemcpyAsync(my_flags + word, &mg->generation_pinned[0], sizeof(unsigned), cudaMemcpyHostToDevice, stream),
+                          "flag write");
     for (int q = 0; q < W; q++) {
       if (q == R) continue;
       if (!host_cuda_ok(cudaMemcpyAsync(reinterpret_cast<unsigned *>(mg->peer[q]) + word, my_flags + GEN_WORD, sizeof(unsigned),
@@ -385,7 +398,7 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
       // this rank's replica is about to be overwritten: every peer must have finished reading last call's contents
       if (gen > 1)
         for (int q = 0; q < W; q++)
-          if (q != R && !wait_flag(sin, my_flags + done_word(q), gen - 1)) return false;
+          if (q != R && !wait_flag(sin, q, done_word(q), gen - 1)) return false;
     }
     auto window = [&](int q, size_t &c0, size_t &cn) {
       int f, c;
@@ -408,13 +421,14 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
       for (int i = 1; i < W; i++) {
         const int q = (R + i) % W;  // every rank starts with a different peer
         window(q, c0, cn);
-        if (!wait_flag(spull, my_flags + arrived_word(q, p), gen)) return false;
+        if (!wait_flag(spull, q, arrived_word(q, p), gen)) return false;
         if (cn == 0) continue;
         const size_t off = c0 * lda + row0;
         const double *src = reinterpret_cast<const double *>(mg->peer[q] + FLAG_PAGE_BYTES) + off;
         if (!host_cuda_ok(cudaMemcpy2DAsync(dA + off, sizeof(double) * lda, src, sizeof(double) * lda, sizeof(double) * rows, cn,
                                             cudaMemcpyDeviceToDevice, spull), "peer pull of A"))
           return false;
+        if (hooks.mark) hooks.mark(spull, "pull", p, q);
       }
     }
     return true;

@@ -1,7 +1,7 @@
 """Worker for the multi-GPU host-buffer column split (rtat_b200_mg_dgemm_host): run under torch.distributed.run with one
 rank per GPU, or directly (world 1).  Every rank holds the full host A and its column block of B; the result is checked
 against torch's float64 matmul on the device within the DGEMM bound 2 k eps (|A||B|), for two different A in a row (the second
-call reuses the replicas, so it exercises the 'peers are done reading' flags) and for both spin-wait and stream-memop waits."""
+call reuses the replicas, so it exercises the 'peers are done reading' flags) and for the three flag transports (mg.signal / mg.spin_wait)."""
 import os
 import sys
 
@@ -26,17 +26,19 @@ def main():
     cs = rt.ColumnSplit(handle, rank, world)
     cases = [(0, 0, 4096, 1024 * world, 4096), (1, 0, 1000, 700 * world + 3, 3000), (0, 1, 2500, 512 * world, 2304), (0, 0, 300, 40 * world, 77)]
     max_bytes = max((k if ta else m) * (m if ta else k) * 8 for ta, _, m, _, k in cases)
-    hb = cs.host_setup(max_bytes)
-    if world > 1:
-        mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
-        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allh, mine)
-        cs.host_connect(allh.cpu().numpy().tobytes())
-    else:
-        cs.host_connect(None)
     eps = np.finfo(np.float64).eps
-    for spin in (0, 1):
+    for signal, spin in ((1, 0), (0, 0), (0, 1)):  # flags polled in the writer's page; pushed + stream memops; pushed + polling kernels
+        # the flag transport is a property of a set-up exchange (who writes which page): a fresh setup per transport
+        handle.set_option("mg.signal", signal)
         handle.set_option("mg.spin_wait", spin)
+        hb = cs.host_setup(max_bytes)
+        if world > 1:
+            mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
+            allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine)
+            cs.host_connect(allh.cpu().numpy().tobytes())
+        else:
+            cs.host_connect(None)
         for ci, (ta, tb, m, n, k) in enumerate(cases):
             first, n_loc = rt.mg.partition(n, world, rank)
             ar, ac = (k, m) if ta else (m, k)
@@ -69,6 +71,9 @@ def main():
                 assert bool((got[:, m:] == 3.0).all()), "ldc padding rows must be untouched"
                 if dist:
                     dist.barrier()
+        if dist:
+            dist.barrier()  # nobody is still pulling from a replica that is about to be freed
+        cs.host_teardown()
     cs.close()
     handle.close()
     print(f"mg_host ok rank {rank}/{world}", flush=True)

@@ -57,9 +57,11 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
  * The multi-GPU counterpart of rtat_b200_dgemm_host (rtat_b200.h).  Every rank passes the same full A and its own column
  * block of op(B) / C.  A crosses PCIe ONCE per step in total: for every K-panel each rank uploads only its 1/world share
  * into its replica of A, publishes a flag, and pulls the other shares from the peers' replicas over NVLink with the copy
- * engines (replicas are IPC-mapped into every process).  Flags are 4-byte peer copies, waits are stream memory operations
- * (cuStreamWaitValue32; a one-thread polling kernel with a 30 s timeout where the driver lacks them), so the exchange uses
- * no SM and needs no process-group collective inside the step.  Around that exchange the schedule is the single-GPU host
+ * engines (replicas are IPC-mapped into every process).  A flag is a generation number in the WRITER's own page, set by a
+ * 4-byte H2D copy queued behind the upload; a reader polls it over NVLink with a one-thread kernel (30 s timeout -> error
+ * status), so nothing is ever pushed across GPUs and the step needs no process-group collective.  (Option "mg.signal" = 0,
+ * read by _host_setup, selects the first design instead — flags pushed with 4-byte peer copies, waits as stream memory
+ * operations — which measured 20 % slower: the pushed words land late.)  Around that exchange the schedule is the single-GPU host
  * pipeline: K-panels of A against the leading column blocks while A is still arriving, then whole-K column blocks with
  * their C blocks streaming back to the host.
  *

@@ -398,6 +398,9 @@ def main():
             handle.set_option("mg.spin_wait", 1)
         if os.environ.get("RTAT_B200_HOST_TRACE"):  # per-stage timeline of every host-entry call on stderr
             handle.set_option("host.trace", 1)
+        for kv in filter(None, os.environ.get("RTAT_B200_E2E_OPTIONS", "").split(",")):  # experiments: "host.lead=3,dgemm.tile=64"
+            key, val = kv.split("=")
+            handle.set_option(key.strip(), int(val))
         if world > 1 and transport != "nccl-broadcast" and mg_mode != "percall":
             # host-buffer column split: every rank uploads 1/world of each K-panel of A into its replica and pulls the other
             # shares from the peers' replicas over NVLink (copy engines, flag-synchronised) — A crosses PCIe once per step

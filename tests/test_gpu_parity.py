@@ -382,7 +382,7 @@ def test_gemm_host_entry_k_panel_pipeline(handle, ta, tb):
     hC = C0.clone()
     launches = handle.launch_count()
     handle.gemm(True, ta, tb, m, n, k, alpha, hA, lda, hB, ldb, beta, hC, ldc, host=True)
-    assert handle.launch_count() - launches > 3, "expected one GEMM per (column block, K-panel) of the leading blocks"
+    assert handle.launch_count() - launches >= 3, "expected one GEMM per K-panel under the leading blocks (3 panels here)"
     Am = hA.view(ac, lda).t()[:ar].cuda()
     Bm = hB.view(bc, ldb).t()[:br].cuda()
     opA, opB = (Am.t() if ta else Am), (Bm.t() if tb else Bm)

@@ -336,6 +336,45 @@ def test_dgemm_config5_column_block(handle):
     _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)
 
 
+@pytest.mark.parametrize("tile", [64, 128])
+def test_dgemm_ragged_tiles_every_residue_class(handle, tile):
+    """The consumers of a ragged tile skip the DMMA blocks (64x64 tiles) or whole warps (128x128) that lie outside C, and the
+    ragged tiles are scheduled after the full ones: residues on either side of every 8 / 16 / 32 / 64 boundary, both operand
+    orientations (8-row blocks for a K-contiguous operand, pairs of blocks for an M/N-contiguous one), k long enough for
+    the stream-K split (kt >= 8); C starts as NaN so an element nobody wrote is caught."""
+    handle.set_option("dgemm.tile", tile)
+    try:
+        res = [1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 57, 63, 65, 100, 127]
+        for i, rm in enumerate(res):
+            rn = res[(i * 7 + 3) % len(res)]
+            ta, tb = OPS[i % 4]
+            _full_size_vs_cublas(handle, np.float64, ta, tb, 3 * tile + rm, 2 * tile + rn, 160 + i, 9200 + i)
+        # many ragged tiles against few full ones, and the corner tile alone
+        _full_size_vs_cublas(handle, np.float64, 0, 1, 20 * tile + 1, tile + 57, 2049, 9301)
+        _full_size_vs_cublas(handle, np.float64, 1, 0, tile - 3, tile - 5, 300, 9302)
+    finally:
+        handle.set_option("dgemm.tile", 0)
+
+
+def test_dgemm_l2_eviction_hints_do_not_change_results(handle):
+    m, n, k = 1500, 1300, 700
+    A = torch.empty(m * k, dtype=torch.float64, device="cuda")
+    B = torch.empty(k * n, dtype=torch.float64, device="cuda")
+    handle.fill_uniform(A, 5)
+    handle.fill_uniform(B, 6)
+    out = []
+    try:
+        for hints in (0, 1):
+            handle.set_option("dgemm.l2_hints", hints)
+            Cm = torch.full((m * n,), float("nan"), dtype=torch.float64, device="cuda")
+            handle.gemm(True, 0, 0, m, n, k, 1.0, A, m, B, k, 0.0, Cm, m)
+            assert "tma" in handle.last_kernel()
+            out.append(Cm)
+    finally:
+        handle.set_option("dgemm.l2_hints", 0)
+    assert torch.equal(out[0], out[1])
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_gemm_extreme_aspect_ratios(handle, dtype):
     """Degenerate-looking shapes stress the schedules rather than the math: one tile with a very long k (every CTA of the

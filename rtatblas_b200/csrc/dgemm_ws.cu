@@ -774,7 +774,12 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
     double t128 = padded(128) / (tma ? 0.98 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
     long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16) / (tri ? 2 : 1);
     bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
-    tile_cfg = (small || t64 < t128) ? 64 : 128;
+    // With TMA producers, two resident 64x64 CTAs hide each other's epilogues and tile switches; a 128x128 CTA idles its DMMA
+    // pipe during both.  The short-k products of the blocked callers (TRSM updates, K-panels of the host and multi-GPU
+    // pipelines) sit here; only from k ~ 8192 on does the larger tile's lower shared-memory traffic win
+    // (profiles/r01_perf_edges.txt: 64x64 ahead by 0.5-2 % up to k = 4096, 128x128 ahead by 4 % at 8192^3).
+    bool shallow = tma && !tri && k <= 4096;
+    tile_cfg = (small || shallow || t64 < t128) ? 64 : 128;
   }
   if (tile_cfg == 64)
     return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);

@@ -14,6 +14,11 @@
 //   * a store thread TMA-stores the staged tile (bulk tensor store clips ragged edges, loads
 //     zero-fill them, so no edge code exists).
 // All global traffic is full-line TMA; the SM's LSU only ever touches shared memory.
+//
+// A_CPASYNC variant: A has an odd leading dimension or an 8 B / 4 B aligned base (config 3: ld 4097, 3001), which TMA cannot
+// address, but C (a padded scratch matrix in the pad plans) and B can.  Four producer warps then fill the same swizzled
+// ring with element-sized cp.async copies (coalesced along A's contiguous dimension, zero-filled outside A) that complete
+// on the same mbarriers; transposers and the TMA store path are unchanged.
 #include <cuda.h>
 #include "common.cuh"
 
@@ -23,6 +28,7 @@ namespace gt {
 constexpr int TILE = 64;
 constexpr int IN_STAGES = 3, OUT_STAGES = 3;
 constexpr int THREADS = 320;  // 8 transpose warps + a TMA load warp + a TMA store warp
+constexpr int PRODUCER_THREADS = 128, THREADS_CPASYNC = THREADS + PRODUCER_THREADS;  // + 4 cp.async producer warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
@@ -53,6 +59,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                : "memory");
 }
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(dst), "l"(src), "n"(BYTES), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ T combine(T alpha, T a, T beta, T b, bool use_b);
 template <>
@@ -70,12 +84,19 @@ struct Params {
   int m, n;  // C is m x n; A is n x m
   int tiles_m, tiles_n;
   double alpha, beta;  // converted to T in the kernel
+  const void *A;       // A_CPASYNC only
+  int lda;
+  // The bulk tensor store clips at 16 B granularity (measured: with m = 517 doubles it also wrote row 517), so mapC covers
+  // only the m_store = m rounded down to a 16 B multiple leading rows and the transposers store the last m - m_store
+  // (< 16 B worth of) rows themselves.
+  void *C;
+  int ldc, m_store;
 };
 
 // mapA: dims {n (contiguous), m}, box {ROW, 64}.  mapB / mapC: dims {m (contiguous), n}, box {ROW, 64}.
 // ROW = 128 B worth of elements.
-template <typename T, bool USE_B>
-__global__ void __launch_bounds__(THREADS, 1)
+template <typename T, bool USE_B, bool A_CPASYNC>
+__global__ void __launch_bounds__(A_CPASYNC ? THREADS_CPASYNC : THREADS, 1)
 geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                           const __grid_constant__ CUtensorMap mapC, const Params p) {
   constexpr int ROW = 128 / sizeof(T);        // elements per 128 B smem row (16 doubles / 32 floats)
@@ -94,7 +115,7 @@ geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < IN_STAGES; s++) {
-      mbar_init(in_full + 8 * s, 1);
+      mbar_init(in_full + 8 * s, A_CPASYNC ? PRODUCER_THREADS : 1);
       mbar_init(in_empty + 8 * s, 8);
     }
     for (int s = 0; s < OUT_STAGES; s++) {
@@ -114,9 +135,11 @@ geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       uint32_t iphase = 0, ophase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int i0 = int(tile % p.tiles_m) * TILE, j0 = int(tile / p.tiles_m) * TILE;
-        mbar_wait(in_empty + 8 * is, iphase ^ 1);
-        mbar_arrive_expect_tx(in_full + 8 * is, TILE_BYTES);
-        for (int b = 0; b < BOXES; b++) tma_load_2d(in0 + is * TILE_BYTES + b * BOX_BYTES, &mapA, j0 + b * ROW, i0, in_full + 8 * is);
+        if (!A_CPASYNC) {
+          mbar_wait(in_empty + 8 * is, iphase ^ 1);
+          mbar_arrive_expect_tx(in_full + 8 * is, TILE_BYTES);
+          for (int b = 0; b < BOXES; b++) tma_load_2d(in0 + is * TILE_BYTES + b * BOX_BYTES, &mapA, j0 + b * ROW, i0, in_full + 8 * is);
+        }
         if (USE_B) {
           mbar_wait(out_free + 8 * os, ophase ^ 1);  // the store that last used this staging buffer has read it
           mbar_arrive_expect_tx(b_full + 8 * os, TILE_BYTES);
@@ -147,6 +170,36 @@ geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     return;
   }
 
+  if (A_CPASYNC && warp >= 10) {
+    // ===================== cp.async producers for A (4 warps) =====================
+    // thread pt owns column jj = pt % 64 of the tile (A's contiguous dimension: a warp copies 32 consecutive elements of
+    // one row) and rows pt / 64 + 2 r; the swizzled destination is what the TMA box layout would have produced
+    const int pt = threadIdx.x - 10 * 32, jj = pt % TILE, ii0 = pt / TILE;
+    const T *Ab = static_cast<const T *>(p.A);
+    const uint32_t dst_col = (jj / ROW) * BOX_BYTES + (jj % EPC) * sizeof(T);
+    const uint32_t chunk = (jj % ROW) / EPC;
+    int is = 0;
+    uint32_t iphase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int i0 = int(tile % p.tiles_m) * TILE, j0 = int(tile / p.tiles_m) * TILE;
+      mbar_wait(in_empty + 8 * is, iphase ^ 1);
+      const uint32_t in = in0 + is * TILE_BYTES + dst_col;
+      const bool jok = j0 + jj < p.n;
+      const T *src = Ab + (size_t)(i0 + ii0) * p.lda + (j0 + jj);
+#pragma unroll 8
+      for (int r = 0; r < TILE / 2; r++) {
+        const int i = ii0 + 2 * r;
+        const bool ok = jok && i0 + i < p.m;
+        cp_async_zfill<sizeof(T)>(in + i * 128 + ((chunk ^ (i & 7)) << 4), ok ? src : Ab, ok ? (int)sizeof(T) : 0);
+        src += 2 * (size_t)p.lda;
+      }
+      cp_async_mbar_arrive_noinc(in_full + 8 * is);
+      if (++is == IN_STAGES) { is = 0; iphase ^= 1; }
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    return;
+  }
+
   // ===================== transpose warps =====================
   int is = 0, os = 0;
   uint32_t iphase = 0, ophase = 0;
@@ -154,6 +207,8 @@ geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   const int i = t % TILE;     // row of the input tile (= index along C's contiguous dimension)
   const int c_first = t / TILE;  // 0..3
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int gi = int(tile % p.tiles_m) * TILE + i, j0 = int(tile / p.tiles_m) * TILE;
+    const bool tail_row = gi >= p.m_store && gi < p.m;  // a row the TMA store cannot clip exactly
     mbar_wait(in_full + 8 * is, iphase);
     if (USE_B) mbar_wait(b_full + 8 * os, ophase);
     else mbar_wait(out_free + 8 * os, ophase ^ 1);
@@ -192,6 +247,7 @@ geam_transpose_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         const T r = combine<T>(alpha, v[e], beta, b, USE_B);
         if (sizeof(T) == 8) asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(dst), "d"((double)r) : "memory");
         else asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(dst), "f"((float)r) : "memory");
+        if (tail_row && j0 + j < p.n) static_cast<T *>(p.C)[(size_t)(j0 + j) * p.ldc + gi] = r;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // staged tile -> visible to the TMA store
@@ -225,9 +281,15 @@ static bool make_map(CUtensorMap *map, const T *base, uint64_t dim0, uint64_t di
 }  // namespace gt
 
 template <typename T>
+static bool tma_addressable(const T *ptr, int ld) {
+  return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ((size_t)ld * sizeof(T)) % 16 == 0;
+}
+
+// A may be anything (cp.async producers take over when TMA cannot address it); C and B must be TMA-addressable.
+template <typename T>
 bool geam_transpose_tma_supported(int m, int n, const T *A, int lda, const T *B, int ldb, const T *C, int ldc, bool use_b) {
-  auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ((size_t)ld * sizeof(T)) % 16 == 0; };
-  if (!ok(A, lda) || !ok(C, ldc) || (use_b && !ok(B, ldb))) return false;
+  (void)A; (void)lda;
+  if (!tma_addressable(C, ldc) || (use_b && !tma_addressable(B, ldb))) return false;
   return (long long)m * n >= 256 * 256;  // below that a persistent TMA pipeline is all prologue
 }
 
@@ -236,24 +298,32 @@ template <typename T>
 int geam_transpose_tma(rtat_b200_context *h, int m, int n, T alpha, const T *A, int lda, T beta, const T *B, int ldb, T *C, int ldc) {
   using namespace gt;
   const bool use_b = beta != T(0);
+  const bool a_tma = tma_addressable(A, lda) && opt(h, "geam.force_cpasync") == 0;
   CUtensorMap ma, mb, mc;
-  bool ok = make_map<T>(&ma, A, n, m, lda) && make_map<T>(&mc, C, m, n, ldc);
+  const int m_store = m / (int)(16 / sizeof(T)) * (int)(16 / sizeof(T));
+  bool ok = m_store > 0 && make_map<T>(&mc, C, m_store, n, ldc);
+  if (a_tma) ok = ok && make_map<T>(&ma, A, n, m, lda);
+  else ma = mc;
   if (use_b) ok = ok && make_map<T>(&mb, B, m, n, ldb);
   else mb = mc;
   if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  Params p{m, n, (m + TILE - 1) / TILE, (n + TILE - 1) / TILE, (double)alpha, (double)beta};
+  Params p{m, n, (m + TILE - 1) / TILE, (n + TILE - 1) / TILE, (double)alpha, (double)beta, A, lda, C, ldc, m_store};
   constexpr int tile_bytes = TILE * TILE * sizeof(T);
   const size_t smem = (size_t)(IN_STAGES + OUT_STAGES) * tile_bytes + 1024 + 256;
   long long tiles = (long long)p.tiles_m * p.tiles_n;
   int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
   // one mask per instantiation (the two kernels share a function-pointer type, so a generic lambda would share one)
-  static std::atomic<uint64_t> configured[2];
-  auto launch = [&](auto kern, std::atomic<uint64_t> &done) {
+  static std::atomic<uint64_t> configured[4];
+  auto launch = [&](auto kern, std::atomic<uint64_t> &done, int threads, const char *name) {
     if (int st = configure_dynamic_smem(kern, smem, h->device, done)) return st;
-    kern<<<grid, THREADS, smem, h->stream>>>(ma, mb, mc, p);
-    return check_launch(h, use_b ? "geam_transpose_tma_accumulate" : "geam_transpose_tma");
+    kern<<<grid, threads, smem, h->stream>>>(ma, mb, mc, p);
+    return check_launch(h, name);
   };
-  return use_b ? launch(geam_transpose_tma_kernel<T, true>, configured[1]) : launch(geam_transpose_tma_kernel<T, false>, configured[0]);
+  if (!a_tma)
+    return use_b ? launch(geam_transpose_tma_kernel<T, true, true>, configured[3], THREADS_CPASYNC, "geam_transpose_cpasync_tma_accumulate")
+                 : launch(geam_transpose_tma_kernel<T, false, true>, configured[2], THREADS_CPASYNC, "geam_transpose_cpasync_tma");
+  return use_b ? launch(geam_transpose_tma_kernel<T, true, false>, configured[1], THREADS, "geam_transpose_tma_accumulate")
+               : launch(geam_transpose_tma_kernel<T, false, false>, configured[0], THREADS, "geam_transpose_tma");
 }
 
 template bool geam_transpose_tma_supported<double>(int, int, const double *, int, const double *, int, const double *, int, bool);

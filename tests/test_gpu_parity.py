@@ -209,6 +209,53 @@ def test_geam_transpose_paths_agree_bitwise(oracle, handle):
         assert np.array_equal(outs[0][0].reshape(n, m), host(A).reshape(m, n).T)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_geam_transpose_of_unaligned_source_into_padded_target(oracle, handle, dtype):
+    """Config 3's transposing pad plans: A has an odd leading dimension (TMA cannot address it), the padded target can be
+    TMA-stored.  cp.async producers fill the TMA kernel's ring; bit-exact against the oracle for move (beta = 0, NaN in the
+    target) and accumulate, ragged edge tiles, an element-aligned base pointer, and against the all-TMA path."""
+    ld_unit = 16 // np.dtype(dtype).itemsize
+    for (m, n, lda_pad, beta, offset) in [(517, 300, 1, 0.0, 0), (300, 517, 0, 0.0, 0), (1024, 257, 0, -0.75, 0), (640, 512, 0, 0.0, 1),
+                                          (2049, 1301, 0, 1.0, 0)]:
+        ldc_pad = (-m) % 32 if offset == 0 else 0
+        if offset:  # base moved by one element: the target must stay 16 B aligned, so only A is offset here
+            ar, ac = n, m
+            lda, ldc = ar + lda_pad, m
+            A = oracle.fill(lda * ac + 1, 90 + m, dtype)
+            C0 = np.full(ldc * n, np.nan, dtype=dtype)
+            dA, dC = dev(A), dev(C0)
+            handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, dA.data_ptr() + A.itemsize, lda, 0.0, dC, ldc, dC, ldc)
+            assert handle.last_kernel() == "geam_transpose_cpasync_tma", handle.last_kernel()
+            exp = C0.copy()
+            oracle.geam(1, 0, m, n, dtype(1.0), A[1:], lda, dtype(0.0), exp, ldc, exp, ldc)
+            assert np.array_equal(host(dC).view(np.uint8), exp.view(np.uint8))
+            continue
+        assert (n + lda_pad) % ld_unit != 0
+        _geam_case(oracle, handle, dtype, 1, 0, m, n, 1.0, beta, 80 + m, lda_pad=lda_pad, ldb_pad=ldc_pad, ldc_pad=ldc_pad, inplace=True,
+                   nan_b=(beta == 0.0))
+        assert handle.last_kernel().startswith("geam_transpose_cpasync_tma"), handle.last_kernel()
+    # a row count that is not a multiple of 16 B on the all-TMA path: the bulk store clips at 16 B granularity, so the last
+    # rows are stored by the transposers (this wrote row m of the padded target before)
+    for (m, beta) in [(517, 0.0), (519, 0.5), (513, -1.0)]:
+        pad = (-m) % 32
+        _geam_case(oracle, handle, dtype, 1, 0, m, 300, 1.0, beta, 95 + m, ldb_pad=pad, ldc_pad=pad, inplace=True, nan_b=(beta == 0.0))
+        assert handle.last_kernel().startswith("geam_transpose_tma"), handle.last_kernel()
+    # the producers against the TMA loads on a source both can address
+    m, n = 1000, 1100
+    A = dev(oracle.fill(n * m, 5, dtype))
+    outs = []
+    try:
+        for force in (0, 1):
+            handle.set_option("geam.force_cpasync", force)
+            Cm = torch.full((m * n,), float("nan"), dtype=torch.float64 if dtype == np.float64 else torch.float32, device="cuda")
+            handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, A, n, 0.0, Cm, m, Cm, m)
+            outs.append((host(Cm), handle.last_kernel()))
+    finally:
+        handle.set_option("geam.force_cpasync", 0)
+    assert outs[0][1] == "geam_transpose_tma" and outs[1][1] == "geam_transpose_cpasync_tma"
+    assert np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8))
+
+
 def test_geam_argument_checks(handle):
     x = torch.zeros(64, dtype=torch.float64, device="cuda")
     y = torch.zeros(64, dtype=torch.float64, device="cuda")

@@ -49,6 +49,11 @@ struct TileCfg {
   static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // consumers of a ragged tile skip single DMMA blocks (64x64 tiles) or only whole warps (128x128: at the register cap)
   static constexpr bool FINE_EDGES = BM_ == 64;
+  // 128x128 tiles: the consumers need more registers than an even split of the file gives them (setmaxnreg, see the
+  // kernel); 64x64 tiles hold 64 accumulator registers and do not
+  static constexpr bool SPLIT_REGS = BM_ == 128;
+  // 16-byte fragment loads + permuted k (see kmap) or the original 8-byte scheme (see FragAddr64)
+  static constexpr bool VEC_FRAGS = BM_ == 128;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
 using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
@@ -85,6 +90,7 @@ struct Params {
   // GB, L2 hit rate 78.9 -> 75.7 %, time unchanged (DRAM is at 4 % of its bandwidth either way): the CTAs that share a B
   // panel drift apart in k, and an evict_first line is gone before the laggard asks for it.
   unsigned long long l2_a, l2_b;
+  int a_3d, b_3d;  // the operand's map is the 3-D view (see tma_load_3d)
 };
 
 // Tile t of a triangular enumeration -> (i, j) with i >= j: t = i (i + 1) / 2 + j.
@@ -161,6 +167,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
       : "memory");
 }
+// 3-D form: an M/N-contiguous operand whose contiguous extent is a multiple of 16 is viewed as {16, k, extent / 16}
+// (strides 8 B, ld, 128 B), so ONE box {16, BK, BMN / 16} lands as the same BMN / 16 swizzled [BK][128 B] atoms that
+// BMN / 16 two-dimensional boxes would produce.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void *src, int bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
@@ -172,25 +187,34 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
   return v;
 }
 
-// ---- lane <-> element permutations ----------------------------------------------------------------
-// K-contiguous operand: rows (m or n) are 128 B smem rows swizzled by (row & 7).  Lane index x (0..7)
-// of a DMMA block owns physical row rho(x) of the block.
+// ---- lane <-> element maps ---------------------------------------------------------------------------
+// Fragments are fetched with 16-byte shared loads, two DMMA operands per instruction, and the k indices of a k-tile are
+// dealt to the DMMA steps so that both kinds of operand can do that: step ks, lane q multiplies k = kmap(q, ks).  (Any
+// partition of the 16 k's into four steps of four is a valid DGEMM as long as A and B agree on it.)
+__host__ __device__ constexpr int kmap(int q, int ks) { return 2 * q + (ks & 1) + 8 * (ks >> 1); }
+// K-contiguous operand: rows (m or n) are 128 B smem rows swizzled by (row & 7); lane index x (0..7) of a DMMA block
+// owns physical row rho(x) of the block.  One 16-byte load = k = kmap(q, 2h), kmap(q, 2h + 1): steps 2h and 2h + 1 of one
+// block.  For a fixed q the eight rows hit eight different 16 B chunks: 4 wavefronts per warp load, the minimum.
 __host__ __device__ constexpr int rho(int x) { return 2 * (x & 3) + (x >> 2); }
-// M/N-contiguous operand: 16 consecutive m (or n) form one 128 B smem row per k, swizzled by (k & 7);
-// a pair of DMMA blocks (b = 0,1) shares one 16-wide atom.  Lane index x of block b owns element
-// rho2(b, x) of the atom.
-__host__ __device__ constexpr int rho2(int b, int x) { return 4 * b + (x & 1) + 8 * ((x >> 1) & 1) + 2 * (x >> 2); }
+// M/N-contiguous operand: 16 consecutive m (or n) form one 128 B smem row per k, swizzled by (k & 7).  Lane index x owns
+// elements 2x and 2x + 1 of the atom: blocks 2p and 2p + 1 of atom p.  One 16-byte load = both blocks of one step; the
+// eight lanes of a k-row cover its eight chunks: again 4 wavefronts.
 
 // physical index (within the warp tile) of DMMA block `blk`, lane index x
 template <bool KC>
 __host__ __device__ constexpr int phys_index(int blk, int x) {
-  return KC ? 8 * blk + rho(x) : 16 * (blk / 2) + rho2(blk & 1, x);
+  return KC ? 8 * blk + rho(x) : 16 * (blk / 2) + 2 * x + (blk & 1);
 }
 
 // swizzled byte offset of element (mn, k) of an operand tile (what TMA produces; the cp.async
@@ -201,9 +225,46 @@ __device__ __forceinline__ uint32_t tile_offset(int mn, int k) {
   return (mn >> 4) * (BK * 128) + k * 128 + (((((mn & 15) >> 1) ^ (k & 7)) & 7) << 4) + ((mn & 1) << 3);
 }
 
-// Per-thread fragment addressing for one operand: addr(blk, ks) = base + imm(blk, ks) + off[sel(blk, ks)]
+// Per-thread fragment addressing for one operand: a base, two lane-dependent swizzle terms, immediates for the rest.
+//   KC : pair(blk, h)  -> 16 bytes = steps 2h, 2h + 1 of block blk
+//   !KC: pair(p, ks)   -> 16 bytes = blocks 2p, 2p + 1 of step ks
 template <bool KC>
 struct FragAddr {
+  uint32_t base;
+  uint32_t off[2];
+  __device__ __forceinline__ void init(uint32_t tile_base_warp /* byte offset of the warp's first row */, int q, int x) {
+    if (KC) {
+      const int r = rho(x);
+      base = tile_base_warp + r * 128;
+#pragma unroll
+      for (int h = 0; h < 2; h++) off[h] = uint32_t(((q + 4 * h) ^ r) & 7) << 4;  // chunk k >> 1 = q + 4h
+    } else {
+      base = tile_base_warp + 2 * q * 128;                                          // k-row 2q (+ (ks & 1) + 8 (ks >> 1))
+#pragma unroll
+      for (int e = 0; e < 2; e++) off[e] = uint32_t((x ^ (2 * q + e)) & 7) << 4;   // chunk x, k & 7 = 2q + (ks & 1)
+    }
+  }
+  __device__ __forceinline__ uint32_t pair(int a, int b) const {
+    if (KC) return base + a * 1024 + off[b];
+    return base + a * (BK * 128) + (b & 1) * 128 + (b >> 1) * 1024 + off[b & 1];
+  }
+};
+
+// ---- 8-byte fragment loads (64x64 tiles) ------------------------------------------------------------------
+// The 64x64 configuration keeps the original scheme: one LDS.64 per DMMA operand, k = 4 ks + q.  (The 16-byte scheme
+// above produced a sporadic wrong A fragment in one lane of the TN 64x64 TMA kernel — 2 of 72 runs of the multi-GPU
+// host worker, always the same element, never with 128x128 tiles; the cause was not found within the round, so the
+// proven path stays where the register pressure does not call for the new one.)
+// M/N-contiguous operand: a pair of DMMA blocks (b = 0, 1) shares one 16-wide atom; lane index x of block b owns
+// element rho2(b, x) of the atom.
+__host__ __device__ constexpr int rho2(int b, int x) { return 4 * b + (x & 1) + 8 * ((x >> 1) & 1) + 2 * (x >> 2); }
+template <bool KC>
+__host__ __device__ constexpr int phys_index64(int blk, int x) {
+  return KC ? 8 * blk + rho(x) : 16 * (blk / 2) + rho2(blk & 1, x);
+}
+// Per-thread fragment addressing for one operand: addr(blk, ks) = base + imm(blk, ks) + off[sel(blk, ks)]
+template <bool KC>
+struct FragAddr64 {
   uint32_t base;
   uint32_t off[4];
   __device__ __forceinline__ void init(uint32_t tile_base_warp /* byte offset of the warp's first row */, int q, int x) {
@@ -225,6 +286,30 @@ struct FragAddr {
     return base + (blk >> 1) * (BK * 128) + ks * 512 + off[(blk & 1) | ((ks & 1) << 1)];
   }
 };
+
+// Fragments of steps 2h, 2h + 1 for the first `lim` blocks of an operand: f[e][blk], e = step parity
+template <bool KC, int NBLK, bool ALL>
+__device__ __forceinline__ void load_half(double (&f)[2][NBLK], const FragAddr<KC> &fa, uint32_t sbase, int h, int lim) {
+  if (KC) {
+#pragma unroll
+    for (int blk = 0; blk < NBLK; blk++)
+      if (ALL || blk < lim) {
+        const double2 v = lds128(sbase + fa.pair(blk, h));
+        f[0][blk] = v.x;
+        f[1][blk] = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int p = 0; p < NBLK / 2; p++)
+        if (ALL || 2 * p < lim) {
+          const double2 v = lds128(sbase + fa.pair(p, 2 * h + e));
+          f[e][2 * p] = v.x;
+          f[e][2 * p + 1] = v.y;
+        }
+  }
+}
 
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
@@ -290,7 +375,7 @@ __device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *
 }
 
 template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
-__global__ void __launch_bounds__((Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, Cfg::CTAS_PER_SM)
+__global__ void __launch_bounds__((Cfg::CONSUMER_WARPS + ((USE_TMA && !Cfg::SPLIT_REGS) ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, Cfg::CTAS_PER_SM)
 dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -336,7 +421,14 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     n0 = ((tile % group_size) / gm) * BN;
   };
 
+  // Register file split (setmaxnreg, per warpgroup): every SM sub-partition hosts one producer warp and two consumer warps
+  // (128x128 tiles; SPLIT_REGS), so what the producers give back — a TMA issuer needs next to nothing — lets the
+  // consumers hold 128 accumulator registers plus a whole half k-tile of fragments without spilling.  The producer
+  // warpgroup is always four warps (three of them idle with TMA) because the instruction is warpgroup-wide.
+  constexpr int PRODUCER_REGS = USE_TMA ? 40 : 56;
+  constexpr int CONSUMER_REGS = ((512 - PRODUCER_REGS) / 2 / 8) * 8;
   if (warp >= CONSUMER_WARPS) {
+    if (Cfg::SPLIT_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PRODUCER_REGS));
     // ======================= producer =======================
     int stage = 0;
     uint32_t phase = 0;
@@ -355,12 +447,16 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int k0 = kt * BK;
             if (KCA) {
               tma_load_2d(sA, &mapA, k0, m0, full, p.l2_a);
+            } else if (p.a_3d) {
+              tma_load_3d(sA, &mapA, 0, k0, m0 / 16, full, p.l2_a);
             } else {
 #pragma unroll
               for (int b = 0; b < BM / 16; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 16 * b, k0, full, p.l2_a);
             }
             if (KCB) {
               tma_load_2d(sB, &mapB, k0, n0, full, p.l2_b);
+            } else if (p.b_3d) {
+              tma_load_3d(sB, &mapB, 0, k0, n0 / 16, full, p.l2_b);
             } else {
 #pragma unroll
               for (int b = 0; b < BN / 16; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 16 * b, k0, full, p.l2_b);
@@ -391,13 +487,25 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 
   // ======================= consumers =======================
+  if (Cfg::SPLIT_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CONSUMER_REGS));
   constexpr int MI = WM / 8, NI = WN / 8, KS = BK / 4;
   const int q = lane % 4, g = lane / 4;
   const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+  constexpr bool VEC = Cfg::VEC_FRAGS;
   FragAddr<KCA> fa_addr;
   FragAddr<KCB> fb_addr;
-  fa_addr.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
-  fb_addr.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
+  FragAddr64<KCA> fa64;
+  FragAddr64<KCB> fb64;
+  if (VEC) {
+    fa_addr.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
+    fb_addr.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
+  } else {
+    fa64.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
+    fb64.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
+  }
+  // physical index (within the warp tile) of DMMA block blk, lane index x, under the scheme in use
+  auto row_of = [](int blk, int x) { return VEC ? phys_index<KCA>(blk, x) : phys_index64<KCA>(blk, x); };
+  auto col_of = [](int blk, int x) { return VEC ? phys_index<KCB>(blk, x) : phys_index64<KCB>(blk, x); };
 
   int stage = 0;
   uint32_t phase = 0;
@@ -421,6 +529,61 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int rv = min(max(p.m - m0 - wm0, 0), WM), cv = min(max(p.n - n0 - wn0, 0), WN);
     const int mi_act = KCA ? (rv + 7) / 8 : 2 * ((rv + 15) / 16), ni_act = KCB ? (cv + 7) / 8 : 2 * ((cv + 15) / 16);
     const bool whole = mi_act == MI && ni_act == NI;
+    if (VEC) {
+    static_assert(KS == 4, "two halves of two DMMA steps per k-tile");
+    if (whole || !Cfg::FINE_EDGES) {
+      // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
+      const bool active = whole || (mi_act > 0 && ni_act > 0);
+      for (int kt = seg.kb; kt < seg.ke; kt++) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (active) {
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            double fa[2][MI], fb[2][NI];
+            load_half<KCA, MI, true>(fa, fa_addr, sbase, h, MI);
+            load_half<KCB, NI, true>(fb, fb_addr, sbase, h, NI);
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int i = 0; i < MI; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[e][i], fb[e][j]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
+      for (int kt = seg.kb; kt < seg.ke; kt++) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+        if (mi_act > 0 && ni_act > 0) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            double fa[2][MI], fb[2][NI];
+            load_half<KCA, MI, false>(fa, fa_addr, sbase, h, mi_act);
+            load_half<KCB, NI, false>(fb, fb_addr, sbase, h, ni_act);
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int i = 0; i < MI; i++)
+                if (i < mi_act) {
+#pragma unroll
+                  for (int j = 0; j < NI; j++)
+                    if (j < ni_act) dmma(acc[i][j], fa[e][i], fb[e][j]);
+                }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+
+    } else {
     if (whole || !Cfg::FINE_EDGES) {
       // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
       const bool active = whole || (mi_act > 0 && ni_act > 0);
@@ -430,17 +593,17 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           double fa[2][MI], fb[2][NI];
 #pragma unroll
-          for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa_addr.addr(i, 0));
+          for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa64.addr(i, 0));
 #pragma unroll
-          for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb_addr.addr(j, 0));
+          for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb64.addr(j, 0));
 #pragma unroll
           for (int ks = 0; ks < KS; ks++) {
             const int cur = ks & 1, nxt = cur ^ 1;
             if (ks + 1 < KS) {
 #pragma unroll
-              for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa_addr.addr(i, ks + 1));
+              for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa64.addr(i, ks + 1));
 #pragma unroll
-              for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb_addr.addr(j, ks + 1));
+              for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb64.addr(j, ks + 1));
             }
 #pragma unroll
             for (int i = 0; i < MI; i++)
@@ -463,10 +626,10 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             double fa[MI], fb[NI];
 #pragma unroll
             for (int i = 0; i < MI; i++)
-              if (i < mi_act) fa[i] = lds64(sbase + fa_addr.addr(i, ks));
+              if (i < mi_act) fa[i] = lds64(sbase + fa64.addr(i, ks));
 #pragma unroll
             for (int j = 0; j < NI; j++)
-              if (j < ni_act) fb[j] = lds64(sbase + fb_addr.addr(j, ks));
+              if (j < ni_act) fb[j] = lds64(sbase + fb64.addr(j, ks));
 #pragma unroll
             for (int i = 0; i < MI; i++)
               if (i < mi_act) {
@@ -480,6 +643,8 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+    }
+
     }
 
     if (seg.kb > 0) {
@@ -528,28 +693,28 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     for (int j = 0; j < NI; j++) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        int col = n0 + wn0 + phys_index<KCB>(j, 2 * q + e);
+        int col = n0 + wn0 + col_of(j, 2 * q + e);
         if (col >= p.n) continue;
         double *ccol = p.C + (size_t)col * p.ldc;
         bool ok[MI];
         double old[MI];
 #pragma unroll
         for (int i = 0; i < MI; i++) {
-          int row = m0 + wm0 + phys_index<KCA>(i, g);
+          int row = m0 + wm0 + row_of(i, g);
           ok[i] = row < p.m && !(TRI && (p.tri == 1 ? row < col : row > col));
           old[i] = 0.0;
         }
         if (beta != 0.0) {
 #pragma unroll
           for (int i = 0; i < MI; i++)
-            if (ok[i]) old[i] = ccol[m0 + wm0 + phys_index<KCA>(i, g)];
+            if (ok[i]) old[i] = ccol[m0 + wm0 + row_of(i, g)];
         }
 #pragma unroll
         for (int i = 0; i < MI; i++) {
           if (ok[i]) {
             double v = alpha * acc[i][j][e];
             if (beta != 0.0) v += beta * old[i];
-            ccol[m0 + wm0 + phys_index<KCA>(i, g)] = v;
+            ccol[m0 + wm0 + row_of(i, g)] = v;
           }
         }
       }
@@ -577,6 +742,19 @@ static bool make_map(CUtensorMap *map, const double *base, uint64_t dim0, uint64
   return r == CUDA_SUCCESS;
 }
 
+// {16, cols, rows / 16} view of a column-major rows x cols matrix (rows % 16 == 0), box {16, box_cols, box_rows / 16}
+static bool make_map_3d(CUtensorMap *map, const double *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_cols,
+                        uint32_t box_rows) {
+  cuuint64_t dims[3] = {16, cols, rows / 16};
+  cuuint64_t strides[2] = {ld_elems * sizeof(double), 16 * sizeof(double)};
+  cuuint32_t box[3] = {16, box_cols, box_rows / 16};
+  cuuint32_t estr[3] = {1, 1, 1};
+  auto encode = tensor_map_encoder();
+  if (!encode) return false;
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
 static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap &ma, const CUtensorMap &mb, const char *name) {
   auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
@@ -584,7 +762,8 @@ static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtenso
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
   static std::atomic<uint64_t> configured{0};  // per template instantiation
   if (int st = configure_dynamic_smem(kern, SMEM_BYTES, h->device, configured)) return st;
-  int threads = (CONSUMER_WARPS + (USE_TMA ? 1 : CPASYNC_PRODUCER_WARPS)) * 32;
+  // with setmaxnreg the producer warpgroup is always complete
+  int threads = (CONSUMER_WARPS + ((USE_TMA && !Cfg::SPLIT_REGS) ? 1 : CPASYNC_PRODUCER_WARPS)) * 32;
   kern<<<grid, threads, SMEM_BYTES, h->stream>>>(ma, mb, p);
   return check_launch(h, name);
 }
@@ -605,7 +784,7 @@ static int resident_ctas_per_sm() {
     auto kern = ws::dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     int occ = 0;
-    int threads = (Cfg::CONSUMER_WARPS + (USE_TMA ? 1 : ws::CPASYNC_PRODUCER_WARPS)) * 32;
+    int threads = (Cfg::CONSUMER_WARPS + ((USE_TMA && !Cfg::SPLIT_REGS) ? 1 : ws::CPASYNC_PRODUCER_WARPS)) * 32;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, Cfg::SMEM_BYTES) != cudaSuccess) {
       (void)cudaGetLastError();
       occ = 1;
@@ -728,8 +907,12 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   memset(&ma, 0, sizeof ma);
   memset(&mb, 0, sizeof mb);
   if (use_tma) {
-    bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM) : make_map(&ma, A, m, k, lda, 16, BK);
-    ok = ok && (!tb ? make_map(&mb, B, k, n, ldb, BK, BN) : make_map(&mb, B, n, k, ldb, 16, BK));
+    // M/N-contiguous operands: one 3-D box per stage instead of BMN / 16 two-dimensional ones when the extent allows
+    const bool box3 = opt(h, "dgemm.tma3d", 1) != 0;
+    p.a_3d = !ta && box3 && m % 16 == 0 && make_map_3d(&ma, A, m, k, lda, BK, BM);
+    p.b_3d = tb && box3 && n % 16 == 0 && make_map_3d(&mb, B, n, k, ldb, BK, BN);
+    bool ok = p.a_3d || (ta ? make_map(&ma, A, k, m, lda, BK, BM) : make_map(&ma, A, m, k, lda, 16, BK));
+    ok = ok && (p.b_3d || (!tb ? make_map(&mb, B, k, n, ldb, BK, BN) : make_map(&mb, B, n, k, ldb, 16, BK)));
     if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;  // descriptor out of range (dims >= 2^32): caller falls back
   }
   // kernel name reported through rtat_b200_last_kernel: dgemm_ws_dmma_<tile>_{tma|cpasync8}[_streamk]
@@ -769,17 +952,12 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
       if (m % bm && n % bm) sixteenths += cost(m % bm, n % bm);
       return sixteenths / 16.0 * bm * bm;
     };
-    // measured steady-state efficiencies: TMA producers 0.98 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
+    // measured steady-state efficiencies: TMA producers 0.985 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
     const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
-    double t128 = padded(128) / (tma ? 0.98 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
+    double t128 = padded(128) / (tma ? 0.985 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
     long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16) / (tri ? 2 : 1);
     bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
-    // With TMA producers, two resident 64x64 CTAs hide each other's epilogues and tile switches; a 128x128 CTA idles its DMMA
-    // pipe during both.  The short-k products of the blocked callers (TRSM updates, K-panels of the host and multi-GPU
-    // pipelines) sit here; only from k ~ 8192 on does the larger tile's lower shared-memory traffic win
-    // (profiles/r01_perf_edges.txt: 64x64 ahead by 0.5-2 % up to k = 4096, 128x128 ahead by 4 % at 8192^3).
-    bool shallow = tma && !tri && k <= 4096;
-    tile_cfg = (small || shallow || t64 < t128) ? 64 : 128;
+    tile_cfg = (small || t64 < t128) ? 64 : 128;
   }
   if (tile_cfg == 64)
     return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);

@@ -363,8 +363,8 @@ def main():
     achieved = 2.0 * m * n_loc * k / (k_avg * 1e-3) * 1e-12
     peaks = measured_peaks()
     if dbl:
-        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/r01_kernels_ncu_summary.csv)
-        traffic = {"c2": 9.609254e9 + 541.678848e6, "c1": 0.016817e9, "c3": 0.296067e9 + 100.826368e6}.get(cfg_name)
+        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/r01_dgemm_ws_ncu_summary.csv)
+        traffic = {"c2": 9.668807e9 + 544.913664e6, "c1": 0.016827e9 + 0.002816e6, "c3": 0.385148e9 + 97.243648e6}.get(cfg_name)
         roof = {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
                 "traffic": traffic, "algorithmic_bytes": 8.0 * (m * k + k * n_loc + m * n_loc), "kernel": handle.last_kernel(),
                 "peak_source": "FP64 DMMA.8x8x4 issue peak measured on this pool (profiles/r01_probe_fp64_rates.txt); MEASURED_PEAKS.json has no FP64 entry",

@@ -130,7 +130,20 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
 /* ---- tuning / introspection (no reference counterpart) ------------------------------------------
  * rtat_b200_set_option:  "dgemm.variant", "sgemm.variant", "geam.variant" select a kernel family
  *   explicitly (0 = automatic).  Used by the tests to force every code path and by the planner's
- *   fused/explicit plan dimension.
+ *   fused/explicit plan dimension.  The other keys are switches for A/B measurements and tests; unknown
+ *   keys are stored and ignored.  (Defaults in brackets.)
+ *     dgemm.tile [0]            128 / 64: force the tile configuration of the persistent DGEMM
+ *     dgemm.streamk [1]         0: data-parallel schedule only
+ *     dgemm.tma3d [1]           0: eight 2-D TMA boxes per M/N-contiguous operand stage instead of one 3-D box
+ *     dgemm.l2_hints [0]        1: evict_last / evict_first on the A / B loads (measured: more DRAM traffic)
+ *     dgemm.force_unaligned [0] 1: cp.async producers even when TMA could address the operands
+ *     sgemm.presplit [1]        0: split op(B) into big / small TF32 parts per tile instead of once per call
+ *     geam.force_cpasync [0]    1: cp.async producers in the transposing geam even for a TMA-addressable source
+ *     geam.tune, geam.rounding  launch-shape and rounding experiments of geam (see csrc/geam.cu)
+ *     trsm.base [0]             diagonal-block size of the recursive TRSM (0 = 128)
+ *     host.panels, host.lead    override the schedule of the host-buffer entry points; host.trace = 1 prints
+ *                               the per-stage timeline of every call to stderr
+ *     mg.signal [1], mg.spin_wait [0]   flag transport of the multi-GPU host entry (rtat_b200_mg.h)
  * rtat_b200_last_kernel: name of the kernel variant the most recent call on this handle launched.
  * rtat_b200_launch_count: number of kernel launches issued through this handle so far. */
 int rtat_b200_set_option(rtat_b200_handle_t handle, const char *key, int value);

@@ -151,6 +151,15 @@ int rtat_b200_get_option(rtat_b200_handle_t handle, const char *key, int *value)
 const char *rtat_b200_last_kernel(rtat_b200_handle_t handle);
 uint64_t rtat_b200_launch_count(rtat_b200_handle_t handle);
 
+/* Schedule the host-buffer entry points below would use for a problem (pure host arithmetic: callable without a GPU;
+ * csrc/host_schedule.h).  world = 0: rtat_b200_{d,s}gemm_host; world >= 1: rtat_b200_mg_dgemm_host on `world` GPUs with
+ * n = this rank's column count.  opt_panels / opt_lead as the options host.panels / host.lead (0 = automatic).
+ * out = {blocks, lead, npanels, nb, col0[blocks], cols[blocks], k0[npanels], kc[npanels]}: column blocks of op(B) / C,
+ * how many leading ones take the K-panel phase, and the K-panels of A.  Returns the number of ints written, -1 on a bad
+ * argument or when cap is too small (44 always suffices). */
+int rtat_b200_host_schedule(int elem_size, int transa, int m, int n, int k, int lda, int world, int opt_panels, int opt_lead, int *out,
+                            int cap);
+
 /* ---- host-buffer entry points ---------------------------------------------------------------------
  * Same contract as dgemm/sgemm but A, B, C are HOST pointers (pinned or pageable).  Operands are
  * staged through the handle's device arena (grown on demand) as a pipeline on three streams: large

@@ -16,6 +16,7 @@ from ._capi import (  # noqa: F401
     lib,
     lib_path,
     exported_symbols,
+    host_schedule,
 )
 from ._host import Planner, host_lib, host_lib_path  # noqa: F401
 from . import _mg as mg  # noqa: F401,E402

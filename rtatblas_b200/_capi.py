@@ -33,6 +33,22 @@ def lib():
     return _lib
 
 
+def host_schedule(elem_size, transa, m, n, k, lda, world=0, panels=0, lead=0):
+    """The schedule the host-buffer entry points would use (rtat_b200_host_schedule; pure host arithmetic, no GPU needed):
+    dict with the column blocks [(col0, cols)], how many leading ones take the K-panel phase, and the K-panels [(k0, kc)]."""
+    out = (C.c_int * 64)()
+    got = lib().rtat_b200_host_schedule(elem_size, transa, m, n, k, lda, world, panels, lead, out, 64)
+    if got < 0:
+        raise RtatError("rtat_b200_host_schedule: bad argument")
+    blocks, nlead, npanels, nb = out[0], out[1], out[2], out[3]
+    o = 4
+    col0 = list(out[o:o + blocks]); o += blocks
+    cols = list(out[o:o + blocks]); o += blocks
+    k0 = list(out[o:o + npanels]); o += npanels
+    kc = list(out[o:o + npanels])
+    return {"blocks": list(zip(col0, cols)), "lead": nlead, "panels": list(zip(k0, kc)), "nb": nb}
+
+
 def exported_symbols():
     """Names declared in include/rtat_b200*.h (used by the CPU test that checks the ABI surface)."""
     names = []
@@ -51,6 +67,7 @@ def _declare(L):
     L.rtat_b200_version.restype = i
     L.rtat_b200_status_string.restype = C.c_char_p
     L.rtat_b200_status_string.argtypes = [i]
+    L.rtat_b200_host_schedule.argtypes = [i, i, i, i, i, i, i, i, i, C.POINTER(i), i]
     L.rtat_b200_create.argtypes = [C.POINTER(vp)]
     L.rtat_b200_destroy.argtypes = [vp]
     L.rtat_b200_set_stream.argtypes = [vp, vp]

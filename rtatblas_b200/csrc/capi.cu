@@ -143,6 +143,25 @@ int rtat_b200_get_option(rtat_b200_handle_t h, const char *key, int *value) {
   return RTAT_B200_STATUS_SUCCESS;
 }
 
+int rtat_b200_host_schedule(int elem_size, int transa, int m, int n, int k, int lda, int world, int opt_panels, int opt_lead, int *out,
+                            int cap) {
+  if ((elem_size != 4 && elem_size != 8) || m < 0 || n < 0 || k < 0 || lda < 1 || world < 0 || !out) return -1;
+  const size_t cols_a = transa == RTAT_B200_OP_N ? k : m;
+  const size_t bytes_a = (size_t(elem_size) * lda * cols_a + 511) & ~size_t(511);
+  double share = 1.0, rate = 50e9;
+  if (world > 0) rtat_b200::mg_link_model(world, share, rate);
+  const rtat_b200::HostSchedule sc = rtat_b200::plan_host_schedule(m, n, k, elem_size, bytes_a, share, rate, world > 0, opt_panels, opt_lead);
+  const int need = 4 + 2 * sc.blocks + 2 * sc.npanels;
+  if (need > cap) return -1;
+  int *o = out;
+  *o++ = sc.blocks; *o++ = sc.lead; *o++ = sc.npanels; *o++ = sc.nb;
+  for (int j = 0; j < sc.blocks; j++) *o++ = sc.col0[j];
+  for (int j = 0; j < sc.blocks; j++) *o++ = sc.cols[j];
+  for (int p = 0; p < sc.npanels; p++) *o++ = sc.k0s[p];
+  for (int p = 0; p < sc.npanels; p++) *o++ = sc.kcs[p];
+  return need;
+}
+
 const char *rtat_b200_last_kernel(rtat_b200_handle_t h) { return h ? h->last_kernel : "none"; }
 uint64_t rtat_b200_launch_count(rtat_b200_handle_t h) { return h ? h->launches : 0; }
 

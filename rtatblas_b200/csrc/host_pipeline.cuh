@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
+#include "host_schedule.h"
 
 namespace rtat_b200 {
 
@@ -70,60 +71,11 @@ int gemm_host_pipeline(rtat_b200_context *h, int transa, int transb, int m, int 
       if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return RTAT_B200_STATUS_ALLOC_FAILED;
   }
   cudaStream_t s = h->stream, sin = h->copy_in, sout = h->copy_out;
-  constexpr int MAX_BLOCKS = 8, MAX_PANELS = 8;
-  // Column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128.
-  int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
-  nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
-  int blocks = (n + nb - 1) / nb;
-  int col0[MAX_BLOCKS + 2], cols[MAX_BLOCKS + 2];
-  for (int j = 0; j < blocks; j++) {
-    col0[j] = j * nb;
-    cols[j] = (col0[j] + nb > n) ? n - col0[j] : nb;
-  }
-  // the last block's copy back to the host is the one transfer nothing can hide: halve it
-  if (blocks > 1 && cols[blocks - 1] >= 512) {
-    const int half = cols[blocks - 1] / 2 / 128 * 128;
-    col0[blocks] = col0[blocks - 1] + half;
-    cols[blocks] = cols[blocks - 1] - half;
-    cols[blocks - 1] = half;
-    blocks++;
-  }
-  // Schedule.  Every column block needs all of A, so a plain column-block pipeline idles the GPU while A crosses
-  // PCIe.  Phase 1 therefore runs the first `lead` column blocks K-panel by K-panel: panel p of A and the matching
-  // pieces of those blocks are copied, then multiplied (beta, then 1) while panel p + 1 is in flight.  `lead` is
-  // chosen so that those blocks' math takes about as long as copying A plus their own share of B.  Phase 2 is the
-  // column-block pipeline for the rest (A is resident by then): copy B_j, multiply, copy C_j back.
-  int panels = 1, lead = 0;
-  if (blocks > 1 && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
-    panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
-    const double pcie = hooks ? hooks->pcie_rate : 50e9, share = hooks ? hooks->a_share : 1.0;
-    const double rate = sizeof(T) == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
-    const double t_a = double(bytes_a) * share / pcie, t_b = double(sizeof(T)) * k * nb / pcie, t_mm = 2.0 * m * nb * double(k) / rate;
-    // in units of nb columns (leading blocks are full).  With several GPUs behind one host the link rate is the shaky
-    // figure (they share the host's memory bandwidth) and a K-panel product is as efficient as a whole-K one at these
-    // depths, so the multi-GPU caller gets a margin: one leading block at N = 4 measured 0.934 of the HBM-resident rate
-    lead = t_mm > t_b ? (hooks ? int(1.3 * t_a / (t_mm - t_b)) + 1 : int(t_a / (t_mm - t_b) + 0.5)) : blocks;
-    if (lead < 1) lead = 1;
-    // host.panels / host.lead: overrides for experiments (0 = the choice above)
-    if (opt(h, "host.panels") > 0) panels = opt(h, "host.panels") < MAX_PANELS ? opt(h, "host.panels") : MAX_PANELS;
-    if (opt(h, "host.lead") > 0) lead = opt(h, "host.lead");
-    if (lead > blocks) lead = blocks;
-  }
-  const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
-  // K-panel table; the first panel is split in two so that the math starts after half a panel of A has landed
-  int k0s[MAX_PANELS + 2], kcs[MAX_PANELS + 2], npanels = 0;
-  for (int p0 = 0; p0 < k; p0 += kp) {
-    k0s[npanels] = p0;
-    kcs[npanels++] = p0 + kp > k ? k - p0 : kp;
-  }
-  if (panels > 1 && kcs[0] >= 1024) {
-    for (int p = npanels; p > 1; p--) { k0s[p] = k0s[p - 1]; kcs[p] = kcs[p - 1]; }
-    const int half = kcs[0] / 2 / 16 * 16;
-    k0s[1] = half;
-    kcs[1] = kcs[0] - half;
-    kcs[0] = half;
-    npanels++;
-  }
+  // Schedule (host_schedule.h): column blocks, K-panels and the number of leading blocks that take the K-panel phase.
+  const HostSchedule sc = plan_host_schedule(m, n, k, sizeof(T), bytes_a, hooks ? hooks->a_share : 1.0, hooks ? hooks->pcie_rate : 50e9,
+                                             hooks != nullptr, opt(h, "host.panels"), opt(h, "host.lead"));
+  const int blocks = sc.blocks, lead = sc.lead, npanels = sc.npanels;
+  const int *col0 = sc.col0, *cols = sc.cols, *k0s = sc.k0s, *kcs = sc.kcs;
   cudaEvent_t *ev = h->host_events;
   int next_event = 1;  // [0] is the entry fence
   // host.trace = 1: timestamp every stage of the pipeline (timed events on the three streams) and print the timeline to

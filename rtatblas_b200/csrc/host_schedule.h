@@ -1,0 +1,86 @@
+// Schedule of the host-buffer GEMM pipeline (host_pipeline.cuh): pure host arithmetic, no CUDA, so that it can be
+// inspected (rtat_b200_host_schedule) and tested without a GPU.
+//
+// Column blocks of op(B) / C: at most 8, at least 256 columns each, multiples of 128; the last one is halved because
+// its copy back to the host is the one transfer nothing can hide.  Every column block needs all of A, so a plain
+// column-block pipeline idles the GPU while A crosses PCIe.  Phase 1 therefore runs the first `lead` column blocks
+// K-panel by K-panel: panel p of A and the matching rows of op(B) under those blocks are copied, then multiplied
+// (beta, then 1) while panel p + 1 is in flight.  `lead` is chosen so that those blocks' math takes about as long as
+// copying A plus their own share of B.  Phase 2 is the column-block pipeline for the rest (A is resident by then):
+// copy B_j, multiply, copy C_j back.  The first K-panel is split in two so that the math starts after half a panel.
+#pragma once
+#include <cstddef>
+
+namespace rtat_b200 {
+
+struct HostSchedule {
+  static constexpr int MAX_BLOCKS = 8, MAX_PANELS = 8;
+  int blocks = 0, lead = 0, npanels = 0, nb = 0;
+  int col0[MAX_BLOCKS + 2] = {}, cols[MAX_BLOCKS + 2] = {};  // column blocks of op(B) / C
+  int k0s[MAX_PANELS + 2] = {}, kcs[MAX_PANELS + 2] = {};    // K-panels of A
+};
+
+// elem: sizeof(T).  bytes_a: bytes of A as stored.  a_share: fraction of A that crosses this GPU's PCIe link, pcie_rate:
+// bytes/s that link can expect, multi: the multi-GPU caller (takes a margin on `lead`, see below).  opt_panels /
+// opt_lead: overrides for experiments (0 = the choice made here).
+inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t bytes_a, double a_share, double pcie_rate, bool multi,
+                                       int opt_panels, int opt_lead) {
+  constexpr int MAX_BLOCKS = HostSchedule::MAX_BLOCKS, MAX_PANELS = HostSchedule::MAX_PANELS;
+  HostSchedule sc;
+  int nb = (n + MAX_BLOCKS - 1) / MAX_BLOCKS;
+  nb = ((nb < 256 ? 256 : nb) + 127) / 128 * 128;
+  sc.nb = nb;
+  int blocks = (n + nb - 1) / nb;
+  for (int j = 0; j < blocks; j++) {
+    sc.col0[j] = j * nb;
+    sc.cols[j] = (sc.col0[j] + nb > n) ? n - sc.col0[j] : nb;
+  }
+  if (blocks > 1 && sc.cols[blocks - 1] >= 512) {
+    const int half = sc.cols[blocks - 1] / 2 / 128 * 128;
+    sc.col0[blocks] = sc.col0[blocks - 1] + half;
+    sc.cols[blocks] = sc.cols[blocks - 1] - half;
+    sc.cols[blocks - 1] = half;
+    blocks++;
+  }
+  int panels = 1, lead = 0;
+  if (blocks > 1 && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
+    panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
+    const double rate = elem == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
+    const double t_a = double(bytes_a) * a_share / pcie_rate, t_b = double(elem) * k * nb / pcie_rate, t_mm = 2.0 * m * nb * double(k) / rate;
+    // in units of nb columns (leading blocks are full).  With several GPUs behind one host the link rate is the shaky
+    // figure (they share the host's memory bandwidth) and a K-panel product is as efficient as a whole-K one at these
+    // depths, so the multi-GPU caller gets a margin: one leading block at N = 4 measured 0.934 of the HBM-resident rate
+    lead = t_mm > t_b ? (multi ? int(1.3 * t_a / (t_mm - t_b)) + 1 : int(t_a / (t_mm - t_b) + 0.5)) : blocks;
+    if (lead < 1) lead = 1;
+    if (opt_panels > 0) panels = opt_panels < MAX_PANELS ? opt_panels : MAX_PANELS;
+    if (opt_lead > 0) lead = opt_lead;
+    if (lead > blocks) lead = blocks;
+  }
+  const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
+  int npanels = 0;
+  for (int p0 = 0; p0 < k; p0 += kp) {
+    sc.k0s[npanels] = p0;
+    sc.kcs[npanels++] = p0 + kp > k ? k - p0 : kp;
+  }
+  if (panels > 1 && sc.kcs[0] >= 1024) {
+    for (int p = npanels; p > 1; p--) { sc.k0s[p] = sc.k0s[p - 1]; sc.kcs[p] = sc.kcs[p - 1]; }
+    const int half = sc.kcs[0] / 2 / 16 * 16;
+    sc.k0s[1] = half;
+    sc.kcs[1] = sc.kcs[0] - half;
+    sc.kcs[0] = half;
+    npanels++;
+  }
+  sc.blocks = blocks;
+  sc.lead = lead;
+  sc.npanels = npanels;
+  return sc;
+}
+
+// Link model of the multi-GPU host entry (mg.cu): each of `world` ranks uploads 1 / world of A; the host side of one box
+// sustains about 150 GB/s over all links, one link about 50 GB/s.
+inline void mg_link_model(int world, double &a_share, double &pcie_rate) {
+  a_share = 1.0 / world;
+  pcie_rate = world > 3 ? 150e9 / world : 50e9;
+}
+
+}  // namespace rtat_b200

@@ -383,8 +383,7 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
   bool started = false;
   HostPipelineHooks<double> hooks;
   hooks.dA = dA;
-  hooks.a_share = 1.0 / W;
-  hooks.pcie_rate = W > 3 ? 150e9 / W : 50e9;  // the host side of one box sustains about 150 GB/s over all links
+  rtat_b200::mg_link_model(W, hooks.a_share, hooks.pcie_rate);
   hooks.fetch_a = [&](size_t row0, size_t col0, size_t rows, size_t cols) {
     cudaStream_t sin = h->copy_in, spull = mg->pull_stream;
     const int p = panel++;

@@ -3,18 +3,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1..c5]
 
-One "step" is one tuned GEMM of the workload through the reference-facing API
-(Planning_System::create_plan + ::execute, i.e. rtat.h's surface via include/rtat_b200_host.h) on
-synthetic inputs already resident in HBM.  Rank 0 prints ONE JSON line (see README / DESIGN.md §5).
+One "step" is one tuned GEMM of the workload through the reference-facing API (Planning_System::create_plan +
+::execute, i.e. rtat.h's surface via include/rtat_b200_host.h) on synthetic inputs already resident in HBM.
+Rank 0 prints ONE JSON line.
 
-Workloads (BASELINE.json configs): N = 1 defaults to config 2 (DGEMM 8192^3 op TN, the configuration
-the metric is quoted on: planner picks between the explicit-transpose plan TNN and the fused plan
-NNN); N > 1 runs config 5 (DGEMM 32768^3, C's columns split across the N GPUs, A broadcast over
-NCCL each step) and reports strong scaling.
+Headline workload (every N): BASELINE config 5, DGEMM 32768^3 — the largest single-GPU configuration and the one the
+column split shards, so N = 1, 2, 4, 8 are the same problem (strong scaling).  At N = 1 it runs through the planner on one
+GPU; at N > 1 C's columns are split across the ranks and A is replicated from rank 0 every step (NVLink copy-engine pulls
+pipelined K-panel by K-panel with the GEMM; NCCL broadcast when peer mapping is unavailable).
 
---impl reference runs the UNMODIFIED reference (oracle/_ref/run_tests = /root/reference/src compiled
-in place against cuBLAS) on the same problem on this GPU and reports its best plan; if that binary
-is missing it falls back to the host-CPU BLAS baseline.
+At N = 1 the line also carries `per_config`: configs 1-4 and the matrix_ops (transpose 8192^2, copy, config 3's pad
+copies), each with value, roofline, a sampled-entry parity check of the timed output against the oracle's exact product,
+and the unmodified reference (oracle/_ref, cuBLAS) timed on the same problem in the same run.
+
+--impl reference runs the UNMODIFIED reference (oracle/_ref/run_tests = /root/reference/src compiled in place against
+cuBLAS) on the same problem on this GPU and reports its best plan; only if that binary is missing does it fall back to the
+host BLAS.
 """
 import argparse
 import json
@@ -37,7 +41,20 @@ CONFIGS = {
     "c4": ("float", "N", "N", 131072, 128, 4096),
     "c5": ("double", "N", "N", 32768, 32768, 32768),
 }
+# (name, rows, cols of the SOURCE, transpose, ld of the target): MatrixMove shapes (reference src/matrix_ops/matrixop.h:307-344)
+MOVES = [
+    ("transpose_8192_f64", 8192, 8192, 1, 8192),
+    ("copy_8192_f64", 8192, 8192, 0, 8192),
+    ("pad_copy_c3_A", 4097, 2049, 0, 4128),
+    ("pad_copy_c3_B", 3001, 2049, 0, 3008),
+]
 DMMA_PEAK_TFLOPS = 37.0  # measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_probe_fp64_rates.txt)
+PARITY_C = {"double": (2.0, 2.0 ** -52), "float": (8.0, 2.0 ** -23)}  # |C - C_exact| <= c k eps (|A||B|), north_star
+
+
+def workload_string(cfg_name, cfg, n=None):
+    dtype, ta, tb, m, nn, k = cfg
+    return f"{cfg_name}: {dtype} GEMM op {ta}{tb} m={m} n={n or nn} k={k} alpha=1 beta=0"
 
 
 def measured_peaks():
@@ -91,7 +108,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_blas_baseline(cfg, budget_s=12.0):
+# ---- CPU baselines (reported only) -----------------------------------------------------------------------
+def cpu_blas_baseline(cfg, budget_s=6.0):
     """Host BLAS (numpy -> OpenBLAS) on a bounded k-slab of the same problem, all host cores."""
     import numpy as np
 
@@ -120,10 +138,12 @@ def cpu_blas_baseline(cfg, budget_s=12.0):
             "sample": f"numpy/OpenBLAS {dtype} GEMM op {ta}{tb} on a {ms}x{ns}x{ks} slab of the {m}x{n}x{k} problem, {reps} reps, all host threads"}
 
 
-def cpu_oracle_baseline(cfg, budget_s=12.0):
+def cpu_oracle_baseline(cfg, budget_s=16.0):
     """The reference's only CPU implementation of this path — the element-wise triple loop its tests check the GPU
     against (tests/common.h:158-193), restated in oracle/oracle.c (OpenMP over columns) — timed on a bounded block of
-    the same problem: a square block of C with the FULL k extent.  The host BLAS figure rides along as `host_blas`."""
+    the same problem: a square block of C with the FULL k extent.  The block is sized from a calibration run (the loop's
+    rate depends strongly on k and the operand strides), so the whole leg stays within budget_s.  The host BLAS figure
+    rides along as `host_blas`."""
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -133,94 +153,165 @@ def cpu_oracle_baseline(cfg, budget_s=12.0):
     dtype, ta, tb, m, n, k = cfg
     npdt = np.float64 if dtype == "double" else np.float32
     cores = os.cpu_count() or 1
-    # size the block for roughly budget_s / 2 at ~0.25 GFLOP/s per core
-    side = int(max(64, min(m, n, (0.5 * budget_s * 0.25e9 * cores / (2.0 * k)) ** 0.5)) // 64 * 64) or min(m, n)
-    ms, ns = min(m, side), min(n, side)
-    ar, ac = (k, ms) if ta == "T" else (ms, k)
-    br, bc = (ns, k) if tb == "T" else (k, ns)
-    A, B = orc.fill(ar * ac, 1, npdt), orc.fill(br * bc, 2, npdt)
-    Cm = np.zeros(ms * ns, dtype=npdt)
-    t0, reps = time.perf_counter(), 0
-    while True:
+
+    def run(side):
+        ms, ns = min(m, side), min(n, side)
+        ar, ac = (k, ms) if ta == "T" else (ms, k)
+        br, bc = (ns, k) if tb == "T" else (k, ns)
+        A, B = orc.fill(ar * ac, 1, npdt), orc.fill(br * bc, 2, npdt)
+        Cm = np.zeros(ms * ns, dtype=npdt)
+        t0 = time.perf_counter()
         orc.gemm(int(ta == "T"), int(tb == "T"), ms, ns, k, 1.0, A, ar, B, br, 0.0, Cm, ms)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s / 2 or reps >= 3:
-            break
-    dt = (time.perf_counter() - t0) / reps
+        return ms, ns, time.perf_counter() - t0
+
+    cal = 2 * cores if 2 * cores >= 32 else 32  # at least a couple of columns per thread
+    cm, cn, ct = run(cal)
+    rate = 2.0 * cm * cn * k / max(ct, 1e-6)
+    want = 0.5 * budget_s  # seconds for the measured block
+    side = int(max(cal, min(m, n, (want * rate / (2.0 * k)) ** 0.5)) // 16 * 16) or cal
+    ms, ns, dt = run(side)
+    if dt < 0.4 * want and side < min(m, n):  # the calibration block under-used the threads: size once more from this run
+        rate = 2.0 * ms * ns * k / max(dt, 1e-6)
+        side = int(max(cal, min(m, n, (want * rate / (2.0 * k)) ** 0.5)) // 16 * 16) or cal
+        ms, ns, dt = run(side)
     out = {"value": 2.0 * ms * ns * k / dt * 1e-12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
            "sample": f"oracle_{'d' if dtype == 'double' else 's'}gemm (the reference's test_gemm triple loop, OpenMP) on the {ms}x{ns} leading block of C "
-                     f"of the {m}x{n}x{k} op {ta}{tb} problem, full k, {reps} reps"}
-    out["host_blas"] = {k2: v for k2, v in cpu_blas_baseline(cfg, budget_s=budget_s / 2).items() if k2 in ("value", "unit", "cores", "sample")}
+                     f"of the {m}x{n}x{k} op {ta}{tb} problem, full k, 1 rep of {dt:.2f} s (block sized from a {cm}x{cn} calibration run)"}
+    out["host_blas"] = {k2: v for k2, v in cpu_blas_baseline(cfg, budget_s=0.25 * budget_s).items() if k2 in ("value", "unit", "cores", "sample")}
     return out
 
 
-# ---------------------------------------------------------------------------------------------------
+# ---- the unmodified reference on this GPU (checker / baseline only) -----------------------------------------
+def reference_run_tests(cfg, reps, warm, timeout=1500):
+    """oracle/_ref/run_tests (the reference's own driver over cuBLAS, exhaustive over its plans) on one problem:
+    {"best_ms", "best_plan", "tflops", "samples"} or None when the binary is absent / the run fails."""
+    dtype, ta, tb, m, n, k = cfg
+    binary = os.path.join(ROOT, "oracle", "_ref", "run_tests")
+    if not os.path.exists(binary):
+        return None
+    method = "gemm_pad" if (m % 32 or n % 32 or k % 32) else "gemm"
+    doc = {"keywords": {"run_type": "exhaustive", "method": method, "data_type": dtype, "repetitions": reps},
+           "problems": [{"transA": ta, "transB": tb, "m": m, "n": n, "k": k}]}
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(doc, f)
+    try:
+        out = subprocess.run([binary, f.name], capture_output=True, text=True, timeout=timeout)
+        res = json.loads(out.stdout)
+        best = None
+        for o in res["problems"][0]["options"]:
+            ts = o["times"][min(warm, reps - 1):] or o["times"]
+            mean = sum(ts) / len(ts)
+            name = "".join(o["option"][x] for x in ("transA", "transB", "transC", "padA", "padB", "padC") if x in o["option"])
+            if best is None or mean < best[0]:
+                best = (mean, name, len(ts))
+        return {"best_ms": best[0], "best_plan": best[1], "samples": best[2], "tflops": 2.0 * m * n * k / (best[0] * 1e-3) * 1e-12,
+                "method": method}
+    except Exception as e:
+        return {"error": str(e)[:200]}
+    finally:
+        os.unlink(f.name)
+
+
+def reference_moves(reps=20):
+    """oracle/_ref/ref_driver time_move: the reference's MatrixMove (cublas?geam) on the matrix_op shapes, event-timed."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(binary):
+        return {}
+    try:
+        out = subprocess.run([binary, "time_move", str(reps)], capture_output=True, text=True, timeout=300)
+        return json.loads(out.stdout)
+    except Exception as e:
+        return {"error": str(e)[:200]}
+
+
 def run_reference(args, cfg_name, cfg, rank, world):
-    """The reference's own driver on this GPU (cuBLAS-backed executor), best plan."""
+    """--impl reference: the reference's own driver on this GPU (cuBLAS-backed executor), best plan."""
     dtype, ta, tb, m, n, k = cfg
     if rank != 0:
         return
-    sample_note = ""
+    note = ""
     if world > 1:
         # the reference is a single-GPU program: give it one rank's column block of the split problem
         n = n // world
-        sample_note = f" (one rank's column block, n/{world})"
+        note = f"one rank's column block (n/{world}) of the split problem: the reference has no multi-GPU path"
     flops = 2.0 * m * n * k
-    reps = args.steps + args.warmup if flops < 5e12 else min(args.steps + args.warmup, 3)
-    binary = os.path.join(ROOT, "oracle", "_ref", "run_tests")
+    # every plan is timed `reps` times, the first `warm` discarded: at least 5 kept samples even for the 2 s problems
+    warm = args.warmup if flops < 5e12 else 3
+    reps = args.steps + warm if flops < 5e12 else min(args.steps, 5) + warm
     line = {"impl": "reference", "metric": "gemm_tflops", "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64" if dtype == "double" else "f32",
-            "data": "synthetic", "config": {"workload": f"{cfg_name}: {dtype} GEMM op {ta}{tb} m={m} n={n} k={k}" + sample_note + " through the reference's run_tests (exhaustive, all plans)"}}
-    if os.path.exists(binary) and (m * k + k * n + m * n) * (8 if dtype == "double" else 4) < 60e9:
-        doc = {"keywords": {"run_type": "exhaustive", "method": "gemm", "data_type": dtype, "repetitions": reps},
-               "problems": [{"transA": ta, "transB": tb, "m": m, "n": n, "k": k}]}
-        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
-            json.dump(doc, f)
-        try:
-            out = subprocess.run([binary, f.name], capture_output=True, text=True, timeout=1500)
-            res = json.loads(out.stdout)
-            best = None
-            for o in res["problems"][0]["options"]:
-                ts = o["times"][min(args.warmup, reps - 1):] or o["times"]
-                mean = sum(ts) / len(ts)
-                name = "".join(o["option"][x] for x in ("transA", "transB", "transC"))
-                if best is None or mean < best[0]:
-                    best = (mean, name)
-            v = flops / (best[0] * 1e-3) * 1e-12
-            line.update({"value": v, "ms_per_step": best[0],
-                         "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
-                                          "sample": f"unmodified reference executor (oracle/_ref/run_tests, cuBLAS 12.9) on this GPU, best plan {best[1]}; the reference has no CPU implementation of the path"},
-                         "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-            line["config"]["world_note"] = "single-GPU program: the reference has no multi-GPU path" if world > 1 else ""
-            print(json.dumps(line), flush=True)
-            return
-        except Exception as e:  # fall through to the CPU baseline
-            line["config"]["reference_gpu_run_failed"] = str(e)[:200]
-        finally:
-            os.unlink(f.name)
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "double" else "f32",
+            "data": "synthetic", "config": {"workload": workload_string(cfg_name, cfg, n)}, "note": note}
+    res = None
+    if (m * k + k * n + m * n) * (8 if dtype == "double" else 4) < 60e9:
+        res = reference_run_tests((dtype, ta, tb, m, n, k), reps, warm)
+    if res and "best_ms" in res:
+        v = res["tflops"]
+        line.update({"value": v, "ms_per_step": res["best_ms"], "samples_per_plan": res["samples"],
+                     "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
+                                      "sample": f"unmodified reference executor (oracle/_ref/run_tests, method {res['method']}, cuBLAS 12.9) on this GPU, best plan "
+                                                f"{res['best_plan']}, mean of {res['samples']} samples; the reference has no CPU implementation of the path"},
+                     "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line), flush=True)
+        return
+    if res:
+        line["reference_gpu_run_failed"] = res.get("error")
     cb = cpu_blas_baseline(cfg, budget_s=20.0)
     line.update({"value": cb["value"], "ms_per_step": flops / (cb["value"] * 1e12) * 1e3, "cpu_baseline": cb,
                  "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
 
 
+# ---- parity of a timed output: sampled entries against the oracle's exact product ---------------------------
+def sampled_parity(torch, orc, dtype, ta, tb, m, n, k, A, lda, B, ldb, Cm, ldc, samples=40, seed=1):
+    """max over a samples x samples grid of entries of |C - C_exact| / (c k eps (|A||B|) + eps |C_exact|), C_exact and |A||B|
+    from oracle_?gemm_exact (long double) on the gathered rows of op(A) / columns of op(B).  <= 1 passes."""
+    import numpy as np
+
+    c, eps = PARITY_C[dtype]
+    g = torch.Generator().manual_seed(seed)
+    rows = torch.unique(torch.cat([torch.tensor([0, m - 1]), torch.randint(0, m, (samples,), generator=g)])).cuda()
+    cols = torch.unique(torch.cat([torch.tensor([0, n - 1]), torch.randint(0, n, (samples,), generator=g)])).cuda()
+    # op(A)[rows, :] as a (len(rows) x k) column-major buffer; op(B)[:, cols] as (k x len(cols)) column-major
+    Av = A.view(-1, lda)  # stored element (r, c) = Av[c, r]
+    if ta:   # A stored k x m: op(A)[i, l] = Av[i, l]
+        sub_a = Av[rows, :k]                       # (r, k): row i of op(A)
+    else:    # A stored m x k: op(A)[i, l] = Av[l, i]
+        sub_a = Av[:k, rows].t()                   # (r, k)
+    Bv = B.view(-1, ldb)
+    if tb:   # B stored n x k: op(B)[l, j] = Bv[l, j]
+        sub_b = Bv[:k, cols]                       # (k, c)
+    else:    # B stored k x n: op(B)[l, j] = Bv[j, l]
+        sub_b = Bv[cols, :k].t()                   # (k, c)
+    r, cc = rows.numel(), cols.numel()
+    # column-major host buffers: (r x k) with ld r  <=> numpy array of shape (k, r) C-contiguous
+    ha = np.ascontiguousarray(sub_a.t().cpu().numpy())
+    hb = np.ascontiguousarray(sub_b.t().cpu().numpy())   # (c, k) C-contiguous <=> (k x c) column-major, ld k
+    exact, absab = orc.gemm_exact(0, 0, r, cc, k, 1.0, ha.reshape(-1), r, hb.reshape(-1), k, 0.0, None, r)
+    got = Cm.view(-1, ldc)[cols][:, rows].t().cpu().numpy().astype(np.float64)   # (r, c)
+    bound = c * k * eps * absab + eps * np.abs(exact)
+    ratio = float(np.max(np.abs(got - exact) / bound))
+    return {"entries": int(r * cc), "max_err_over_bound": ratio, "bound": f"{c:g}*k*eps*(|A||B|) + eps*|C|, eps=2^{-52 if dtype == 'double' else -23}",
+            "pass": bool(ratio <= 1.0)}
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg_name = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
+    cfg_name = args.workload if args.workload != "auto" else "c5"
     cfg = CONFIGS[cfg_name]
 
     if args.impl == "reference":
@@ -240,37 +331,218 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding  # the checker for the sampled parity of the timed outputs (never on the measured path)
+
+    orc = oracle_binding.load()
+    stream = torch.cuda.current_stream()
+    handle = rt.Handle(stream=stream)
+    peaks = measured_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def timed(fn, steps, flush):
+        """per-step CUDA-event times (ms) on the launching stream; `flush` rewrites a 512 MB buffer before every step"""
+        ev = []
+        for _ in range(steps):
+            if flush:
+                flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    def gemm_roofline(dtype, name, achieved_tf, kernel, m, n, k, k_ms):
+        esz = 8 if dtype == "double" else 4
+        alg_bytes = float(esz) * (m * k + k * n + m * n)
+        if dtype == "double":
+            return {"bound": "tensor", "achieved": achieved_tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_tf / DMMA_PEAK_TFLOPS,
+                    "traffic": None, "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ms": k_ms,
+                    "peak_source": "FP64 DMMA.8x8x4 issue peak measured on this pool (profiles/r01_probe_fp64_rates.txt); MEASURED_PEAKS.json has no FP64 entry"}
+        # config 4 sits at the HBM / tensor crossover: quote it against the HBM floor (BASELINE.md §3) and give the tensor view alongside
+        gbs = alg_bytes / (k_ms * 1e-3) * 1e-9
+        tf32x3 = peaks.get("bf16_tflops", 1590.0) / 2.0 / 3.0
+        return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ms": k_ms,
+                "tensor_view": {"achieved_tflops": achieved_tf, "peak_3xtf32_tflops": tf32x3, "frac": achieved_tf / tf32x3,
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32) / 3 (three split products per useful one)"},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+
+    def plan_gemm_alone(dtype, plan, ta, tb, m, n, k, A, B, Cm):
+        """The GEMM launch the chosen plan makes, alone: operands moved (transposed / padded to ld % 32 == 0) as the plan's
+        letters say (reference src/methods/gemm.cpp:28-134), then ONE handle.gemm on them.  Returns a closure."""
+        dbl = dtype == "double"
+        tdt = torch.float64 if dbl else torch.float32
+        letters = (plan + "NNN")[:6]
+        pad = lambda x, p: (x + 31) // 32 * 32 if p == "P" else x
+
+        def moved(X, rows, cols, tflag, pflag, t):
+            # stored rows x cols, op flag t; returns (buffer, ld, op flag) after the explicit MatrixMove, if any
+            if tflag != "T" and pflag != "P":
+                return X, rows, t
+            r2, c2 = (cols, rows) if tflag == "T" else (rows, cols)
+            ld2 = pad(r2, pflag)
+            Y = torch.empty(ld2 * c2, dtype=tdt, device="cuda")
+            handle.geam(dbl, int(tflag == "T"), 0, r2, c2, 1.0, X, rows, 0.0, Y, ld2, Y, ld2)
+            return Y, ld2, (t ^ 1 if tflag == "T" else t)
+
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        A2, lda2, ta2 = moved(A, ar, ac, letters[0], letters[3], ta)
+        B2, ldb2, tb2 = moved(B, br, bc, letters[1], letters[4], tb)
+        if letters[2] == "T":   # C^T = op(B)^T op(A)^T into scratch
+            ldc2 = pad(n, letters[5])
+            C2 = torch.empty(ldc2 * m, dtype=tdt, device="cuda")
+            return lambda: handle.gemm(dbl, tb2 ^ 1, ta2 ^ 1, n, m, k, 1.0, B2, ldb2, A2, lda2, 0.0, C2, ldc2)
+        if letters[5] == "P":
+            ldc2 = pad(m, "P")
+            C2 = torch.empty(ldc2 * n, dtype=tdt, device="cuda")
+            return lambda: handle.gemm(dbl, ta2, tb2, m, n, k, 1.0, A2, lda2, B2, ldb2, 0.0, C2, ldc2)
+        return lambda: handle.gemm(dbl, ta2, tb2, m, n, k, 1.0, A2, lda2, B2, ldb2, 0.0, Cm, m)
+
+    def bench_config(name, steps, warmup, samples_per_plan):
+        """one single-GPU config through the planner: tuning (untimed), `steps` timed steps, roofline leg, sampled parity"""
+        dtype, ta_s, tb_s, m, n, k = CONFIGS[name]
+        ta, tb, dbl = int(ta_s == "T"), int(tb_s == "T"), dtype == "double"
+        tdt, esz = (torch.float64, 8) if dbl else (torch.float32, 4)
+        method = "gemm_pad" if name == "c3" else "gemm"  # config 3 is the one where pad/copy plans matter: 64-plan space
+        planner = rt.Planner(method, dtype)
+        planner.set_tests_until_converge(samples_per_plan)
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        A = torch.empty(ar * ac, dtype=tdt, device="cuda")
+        B = torch.empty(br * bc, dtype=tdt, device="cuda")
+        Cm = torch.empty(m * n, dtype=tdt, device="cuda")
+        handle.fill_uniform(A, 0xB200 + 1, -1.0, 1.0)
+        handle.fill_uniform(B, 0xB200 + 2, -1.0, 1.0)
+        plans = planner.plans()
+        free_b, _ = torch.cuda.mem_get_info()
+        need = max([w for w in (planner.workspace(ta, tb, m, n, k, p) for p in plans) if w < 0.6 * free_b] + [0])
+        ws = torch.empty(max(need, 8) // 8, dtype=torch.float64, device="cuda")
+        step = lambda: planner.gemm(handle, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m, ws, need)
+        tune = [step() for _ in range(samples_per_plan * len(plans) + 1)]
+        torch.cuda.synchronize()
+        chosen = tune[-1]
+        in_bytes = (ar * ac + br * bc) * esz
+        flush = in_bytes < 200e6
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        launches0 = handle.launch_count()
+        # the contract's bracket: K steps back to back between two events (flushing, when needed, happens inside and is
+        # subtracted by timing the steps individually)
+        if flush:
+            ms = timed(step, steps, True)
+            total_ms = sum(ms)
+            launches = handle.launch_count() - launches0
+            warm_ms = timed(step, steps, False)
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            total_ms = a.elapsed_time(b)
+            warm_ms = None
+            launches = handle.launch_count() - launches0
+        kernel = handle.last_kernel()
+        ms_per_step = total_ms / steps
+        flops = 2.0 * m * n * k
+        parity = sampled_parity(torch, orc, dtype, ta, tb, m, n, k, A, ar, B, br, Cm, m)
+        # roofline leg: the GEMM launch of the chosen plan, alone
+        alone = plan_gemm_alone(dtype, chosen, ta, tb, m, n, k, A, B, Cm)
+        alone()
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(timed(alone, min(steps, 10), flush))
+        gemm_kernel = handle.last_kernel()
+        stats = planner.statistics()
+        per_plan = {}
+        for o in stats[0]["options"]:
+            pname = "".join(o["option"][x] for x in ("transA", "transB", "transC", "padA", "padB", "padC") if x in o["option"])
+            if o["times"]:
+                per_plan[pname] = round(sorted(o["times"])[len(o["times"]) // 2], 4)
+        if len(per_plan) > 8:
+            per_plan = dict(sorted(per_plan.items(), key=lambda kv: kv[1])[:8])
+        out = {"workload": workload_string(name, CONFIGS[name]), "metric": "gemm_tflops", "unit": "TFLOP/s",
+               "value": flops / (ms_per_step * 1e-3) * 1e-12, "ms_per_step": ms_per_step, "steps": steps, "plan": chosen,
+               "best_ms_per_plan": per_plan, "kernel": kernel, "gpu_launches": launches,
+               "l2_policy": "512 MB written between timed steps (inputs fit in the 126 MB L2)" if flush else "inputs larger than L2 (126 MB): no flush needed",
+               "roofline": gemm_roofline(dtype, name, flops / (k_ms * 1e-3) * 1e-12, gemm_kernel, m, n, k, k_ms),
+               "parity_check": parity}
+        if warm_ms:
+            out["warm_l2"] = {"ms_per_step": statistics.mean(warm_ms), "value": flops / (statistics.mean(warm_ms) * 1e-3) * 1e-12,
+                              "note": "back-to-back steps, inputs L2-resident: the case the reference's harness measures"}
+        planner.close()
+        return out, (A, B, Cm, ar, br)
+
+    def bench_moves():
+        """matrix_ops through the C ABI (what MatrixMove calls): GB/s of 2 rows cols sizeof(T) algorithmic bytes"""
+        res = {}
+        for name, rows, cols, tr, ldo in MOVES:
+            A = torch.empty(rows * cols, dtype=torch.float64, device="cuda")
+            handle.fill_uniform(A, 0xB200 + 7, -1.0, 1.0)
+            orow, ocol = (cols, rows) if tr else (rows, cols)
+            out = torch.empty(ldo * ocol, dtype=torch.float64, device="cuda")
+            fn = lambda: handle.geam(True, tr, 0, orow, ocol, 1.0, A, rows, 0.0, out, ldo, out, ldo)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            nbytes = 2.0 * rows * cols * 8
+            flush = nbytes < 400e6
+            ms = timed(fn, 20, flush)
+            warm = timed(fn, 20, False)
+            t = statistics.median(ms)
+            got = out.view(ocol, ldo)[:, :orow]
+            want = A.view(cols, rows).t() if tr else A.view(cols, rows)
+            exact = bool(torch.equal(got, want))
+            res[name] = {"workload": f"MatrixMove {'transpose' if tr else 'copy'} of {rows}x{cols} f64 into ld {ldo}", "metric": "matrix_op_gbs", "unit": "GB/s",
+                         "value": nbytes / (t * 1e-3) * 1e-9, "ms": t, "kernel": handle.last_kernel(),
+                         "l2_policy": "512 MB written between timed launches" if flush else "operands larger than L2: no flush needed",
+                         "warm_l2_gbs": nbytes / (statistics.median(warm) * 1e-3) * 1e-9,
+                         "roofline": {"bound": "hbm", "achieved": nbytes / (t * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": nbytes / (t * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "algorithmic_bytes": nbytes},
+                         "parity_check": {"bit_exact": exact, "pass": exact}}
+        return res
+
     dtype, ta_s, tb_s, m, n, k = cfg
     ta, tb = int(ta_s == "T"), int(tb_s == "T")
     dbl = dtype == "double"
     tdt = torch.float64 if dbl else torch.float32
     esz = 8 if dbl else 4
-    # column split of C (and of op(B)) across ranks: rank r owns columns [r*n/world, (r+1)*n/world)
-    n_loc = n // world
-    assert n_loc * world == n, "n must divide evenly across ranks"
-    if world > 1:
-        assert not tb, "column split needs op(B) = B so that a column block is a contiguous view"
+    flops = 2.0 * m * n * k
 
-    stream = torch.cuda.current_stream()
-    handle = rt.Handle(stream=stream)
-    method = "gemm_pad" if cfg_name == "c3" else "gemm"  # config 3 is the one where pad/copy plans matter: 64-plan space
-    planner = rt.Planner(method, dtype)
-    # three samples per plan before converging (the reference's default of one sample is easily fooled on
-    # 70 us problems); an extension of Planning_System, see set_tests_until_converge
-    SAMPLES = 3 if method == "gemm" else 1
-    planner.set_tests_until_converge(SAMPLES)
-    ar, ac = (k, m) if ta else (m, k)
-    br, bc = (n_loc, k) if tb else (k, n_loc)
-    B = torch.empty(br * bc, dtype=tdt, device="cuda")
-    Cm = torch.empty(m * n_loc, dtype=tdt, device="cuda")
-    handle.fill_uniform(B, 0xB200 + 2 + rank, -1.0, 1.0)
-    plans = planner.plans()
-    transport, cs, A_src, A_stage = "none", None, None, None
+    # =========================== N == 1: the workload through the planner ===========================
     if world == 1:
-        A = torch.empty(ar * ac, dtype=tdt, device="cuda")
-        handle.fill_uniform(A, 0xB200 + 1, -1.0, 1.0)
+        big = flops > 5e12
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        head, (A, B, Cm, ar, br) = bench_config(cfg_name, args.steps, args.warmup, 1 if (big or cfg_name == "c3") else 3)
+        clocks = sampler.stop()
+        n_loc = n
+        line = {"metric": "gemm_tflops", "value": head["value"], "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64" if dbl else "f32", "data": "synthetic",
+                "config": {"workload": workload_string(cfg_name, cfg)},
+                "details": {"api": "Planning_System::create_plan + execute (rtat.h surface) -> MatrixOp tree -> rtat_b200_* C ABI", "plan": head["plan"],
+                            "plan_meaning": "NNN = transpose/pad fused into the GEMM's loads; T.. / ...P.. = explicit MatrixMove pass first",
+                            "best_ms_per_plan": head["best_ms_per_plan"], "parallelism": "one GPU", "l2_policy": head["l2_policy"],
+                            "pct_of_fp64_dmma_peak": round(100 * head["value"] / DMMA_PEAK_TFLOPS, 2) if dbl else None},
+                "roofline": head["roofline"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "kernel": head["kernel"],
+                "parity_check": head["parity_check"]}
+    # =========================== N > 1: column split ===========================
     else:
-        assert dbl, "the column-split path is DGEMM (config 5)"
+        assert dbl and not tb, "the column-split path is DGEMM with op(B) = B (a column block is a contiguous view)"
+        n_loc = n // world
+        assert n_loc * world == n, "n must divide evenly across ranks"
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = k, n_loc
+        B = torch.empty(br * bc, dtype=tdt, device="cuda")
+        Cm = torch.empty(m * n_loc, dtype=tdt, device="cuda")
+        handle.fill_uniform(B, 0xB200 + 2 + rank, -1.0, 1.0)
 
         class _DevArray:  # zero-copy torch view of memory the C library allocated
             def __init__(self, ptr, count):
@@ -278,6 +550,7 @@ def main():
 
         cs = rt.ColumnSplit(handle, rank, world)
         hb = torch.zeros(rt.mg.HANDLE_BYTES, dtype=torch.uint8, device="cuda")
+        A_src, A_stage, a_ptr = None, None, None
         if rank == 0:
             a_ptr, hbytes = cs.alloc_shared(ar * ac * esz)  # IPC-exportable: the other ranks' copy engines pull from it
             A = torch.as_tensor(_DevArray(a_ptr, ar * ac), device="cuda")
@@ -290,96 +563,74 @@ def main():
         if rank != 0:
             A = torch.empty(ar * ac, dtype=tdt, device="cuda")  # local replica, filled panel by panel every step
             try:
-                peer = cs.open_shared(bytes(hb.cpu().numpy().tobytes()))
-                A_src, A_stage = peer, A
+                if os.environ.get("RTAT_B200_MG_TRANSPORT") == "nccl":
+                    raise rt.RtatError("forced")
+                A_src, A_stage = cs.open_shared(bytes(hb.cpu().numpy().tobytes())), A
             except rt.RtatError:
                 ok.zero_()
+        elif os.environ.get("RTAT_B200_MG_TRANSPORT") == "nccl":
+            ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         transport = "nvlink-p2p-copy-engine-pull" if ok.item() > 0 else "nccl-broadcast"
-    free_b, _ = torch.cuda.mem_get_info()
-    # plans whose scratch fits comfortably; the others are still explored but degrade to the default plan
-    need = 0 if world > 1 else max([w for w in (planner.workspace(ta, tb, m, n_loc, k, p) for p in plans) if w < 0.6 * free_b] + [0])
-    ws = torch.empty(max(need, 8) // 8, dtype=torch.float64, device="cuda")
-    PANELS = 0  # automatic schedule: 1/16, 3/16, 4/16, 8/16 of K
+        if transport == "nccl-broadcast" and rank != 0 and A_src is not None:
+            cs.close_shared(A_src)
+            A_src = A_stage = None
 
-    def step():
-        if world == 1:
-            return planner.gemm(handle, ta, tb, m, n_loc, k, 1.0, A, ar, B, br, 0.0, Cm, m, ws, need)
-        if transport == "nccl-broadcast":
-            dist.broadcast(A, src=0)  # A replicated once per step over NCCL / NVLink
-            handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, A, ar, B, br, 0.0, Cm, m)
-        else:
-            # K-panel pipeline: copy engines pull panel p+1 of A from rank 0 while the DMMA kernel multiplies panel p
-            cs.dgemm(ta, tb, m, n_loc, k, 1.0, A_src, ar, A_stage, B, br, 0.0, Cm, m, panels=PANELS)
-        return "NNN"
+        def step():
+            if transport == "nccl-broadcast":
+                dist.broadcast(A, src=0)  # A replicated once per step over NCCL / NVLink
+                handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+            else:
+                # K-panel pipeline: copy engines pull panel p+1 of A from rank 0 while the DMMA kernel multiplies panel p
+                cs.dgemm(ta, tb, m, n_loc, k, 1.0, A_src, ar, A_stage, B, br, 0.0, Cm, m, panels=0)
 
-    # ---- tuning (untimed): the planner explores every plan once, then converges ------------------------
-    tune = [step() for _ in range(SAMPLES * len(plans) + 1 if world == 1 else 1)]
-    torch.cuda.synchronize()
-    chosen = tune[-1]
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if dist:
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
         dist.barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = handle.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    torch.cuda.synchronize()
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    if dist:
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = handle.launch_count()
+        a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a_ev.record()
+        for _ in range(args.steps):
+            step()
+        b_ev.record()
+        torch.cuda.synchronize()
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = handle.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_name = handle.last_kernel()
-    if dist:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = handle.launch_count() - launches0
+        t = torch.tensor([a_ev.elapsed_time(b_ev)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    flops = 2.0 * m * n * k
-    value = flops / (ms_per_step * 1e-3) * 1e-12
-
-    # ---- roofline: the GEMM kernel alone, CUDA events on its stream ------------------------------------
-    if world > 1 and rank != 0 and transport != "nccl-broadcast":
-        torch.cuda.synchronize()  # A (the local replica) is complete after the last step
-    k_ms = []
-    for _ in range(min(args.steps, 5)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, A, ar, B, br, 0.0, Cm, m)
-        b.record()
-        b.synchronize()
-        k_ms.append(a.elapsed_time(b))
-    k_avg = sum(k_ms) / len(k_ms)
-    achieved = 2.0 * m * n_loc * k / (k_avg * 1e-3) * 1e-12
-    peaks = measured_peaks()
-    if dbl:
-        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/r01_dgemm_ws_ncu_summary.csv)
-        traffic = {"c2": 9.668807e9 + 544.913664e6, "c1": 0.016827e9 + 0.002816e6, "c3": 0.385148e9 + 97.243648e6}.get(cfg_name)
-        roof = {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
-                "traffic": traffic, "algorithmic_bytes": 8.0 * (m * k + k * n_loc + m * n_loc), "kernel": handle.last_kernel(),
-                "peak_source": "FP64 DMMA.8x8x4 issue peak measured on this pool (profiles/r01_probe_fp64_rates.txt); MEASURED_PEAKS.json has no FP64 entry",
-                "hbm_gbs_measured": peaks.get("hbm_gbs")}
-    else:
-        tf32 = peaks.get("bf16_tflops", 1590.0) / 2.0 / 3.0  # 3xTF32: a third of the TF32 rate, itself half of bf16
-        roof = {"bound": "tensor", "achieved": achieved, "peak": tf32, "unit": "TFLOP/s", "frac": achieved / tf32, "traffic": None,
-                "kernel": handle.last_kernel(), "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32) / 3 (3xTF32 split products)"}
+        ms_per_step = float(t.item()) / args.steps
+        value = flops / (ms_per_step * 1e-3) * 1e-12
+        kernel_name = handle.last_kernel()
+        # full-size parity of the timed output, per rank, on sampled entries (A is complete on every rank after the last step)
+        par = sampled_parity(torch, orc, dtype, ta, tb, m, n_loc, k, A, ar, B, br, Cm, m, seed=1 + rank)
+        worst = torch.tensor([par["max_err_over_bound"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        par.update({"max_err_over_bound": float(worst.item()), "pass": bool(worst.item() <= 1.0), "entries": par["entries"] * world,
+                    "note": "every rank checks its own column block; max over ranks"})
+        # roofline: this rank's GEMM alone
+        alone = lambda: handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+        k_ms = statistics.mean(timed(alone, min(args.steps, 3), False))
+        roof = gemm_roofline(dtype, cfg_name, 2.0 * m * n_loc * k / (k_ms * 1e-3) * 1e-12, handle.last_kernel(), m, n_loc, k, k_ms)
+        line = {"metric": "gemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_string(cfg_name, cfg)},
+                "details": {"api": "rtat_b200_mg_dgemm (column split) over rtat_b200_dgemm", "plan": "NNN",
+                            "parallelism": f"column split of C over {world} GPUs, A replicated every step from rank 0 by {transport}"
+                                           + (", 4 K-panels (1/16, 3/16, 4/16, 8/16 of K) pipelined with the GEMM" if transport != "nccl-broadcast" else ""),
+                            "l2_policy": "inputs larger than L2 (126 MB): no flush needed",
+                            "pct_of_fp64_dmma_peak": round(100 * value / (DMMA_PEAK_TFLOPS * world), 2)},
+                "roofline": roof, "gpu_launches": launches, "clocks": clocks, "kernel": kernel_name, "parity_check": par}
 
     # ---- end to end: host buffers through the C ABI, H2D + GEMM + D2H inside the timed region ------------
-    e2e = None
     if not args.no_e2e:
-        # Every rank is on this node, so A (one copy per process here, as a stand-in for a shared host mapping) is read
-        # by every GPU over its own PCIe link: each rank runs the host entry point on its column block, which
-        # pipelines K-panels of A, its block of B and its block of C against the GEMM.
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n_loc, k) if tb else (k, n_loc)
         hA = torch.empty(ar * ac, dtype=tdt, pin_memory=True)
         hB = torch.empty(br * bc, dtype=tdt, pin_memory=True)
         hC = torch.empty(m * n_loc, dtype=tdt, pin_memory=True)
@@ -387,24 +638,16 @@ def main():
         hB.copy_(B)
         torch.cuda.synchronize()
         e_steps = max(1, min(args.steps, 3))
-
-        api = "rtat_b200_dgemm_host (pinned host buffers)"
-        h2d = (ar * ac + br * bc) * esz
-        # experiments: "percall" = every rank uploads all of A; "push" = flags pushed to the peers (stream memops wait); "spin" = push + polling kernels
-        mg_mode = os.environ.get("RTAT_B200_MG_E2E", "")
-        if mg_mode in ("push", "spin"):
-            handle.set_option("mg.signal", 0)
-        if mg_mode == "spin":
-            handle.set_option("mg.spin_wait", 1)
-        if os.environ.get("RTAT_B200_HOST_TRACE"):  # per-stage timeline of every host-entry call on stderr
-            handle.set_option("host.trace", 1)
+        api = f"rtat_b200_{'d' if dbl else 's'}gemm_host (pinned host buffers)"
         for kv in filter(None, os.environ.get("RTAT_B200_E2E_OPTIONS", "").split(",")):  # experiments: "host.lead=3,dgemm.tile=64"
             key, val = kv.split("=")
             handle.set_option(key.strip(), int(val))
-        if world > 1 and transport != "nccl-broadcast" and mg_mode != "percall":
+        if os.environ.get("RTAT_B200_HOST_TRACE"):
+            handle.set_option("host.trace", 1)
+        if world > 1 and transport != "nccl-broadcast":
             # host-buffer column split: every rank uploads 1/world of each K-panel of A into its replica and pulls the other
-            # shares from the peers' replicas over NVLink (copy engines, flag-synchronised) — A crosses PCIe once per step
-            # release the device-resident A of the HBM-resident bench above: the host entry owns its own replicas
+            # shares from the peers' replicas over NVLink (copy engines, flag-synchronised) — A crosses PCIe once per step.
+            # Release the device-resident A of the HBM-resident bench above: the host entry owns its own replicas.
             torch.cuda.synchronize()
             if rank != 0:
                 cs.close_shared(A_src)
@@ -421,15 +664,10 @@ def main():
             api = ("rtat_b200_mg_dgemm_host (pinned host buffers): per K-panel every rank uploads its 1/N share of A and pulls the "
                    "others over NVLink; B/C column blocks over the rank's own PCIe link")
             h2d = (ar * ac + br * bc * world) * esz
-
-            def e2e_step():
-                cs.dgemm_host(ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m)
+            e2e_step = lambda: cs.dgemm_host(ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m)
         else:
             h2d = (ar * ac + br * bc) * world * esz
-
-            def e2e_step():
-                handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m, host=True)
-
+            e2e_step = lambda: handle.gemm(dbl, ta, tb, m, n_loc, k, 1.0, hA, ar, hB, br, 0.0, hC, m, host=True)
         e2e_step()
         torch.cuda.synchronize()
         if dist:
@@ -443,32 +681,45 @@ def main():
             t = torch.tensor([t1], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t1 = float(t.item())
-        e2e = {"value": flops / (t1 * 1e-3) * 1e-12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": m * n * esz,
-               "ms_per_step": t1, "steps": e_steps, "api": api}
+        line["e2e"] = {"value": flops / (t1 * 1e-3) * 1e-12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": m * n * esz,
+                       "ms_per_step": t1, "steps": e_steps, "api": api}
+        del hA, hB, hC
+
+    # ---- N == 1: the other BASELINE configs and the matrix_ops, each beside the unmodified reference -------------
+    if world == 1 and not args.no_per_config and args.workload == "auto":
+        A = B = Cm = None
+        torch.cuda.empty_cache()
+        per = {}
+        plan_steps = {"c1": 50, "c2": 10, "c3": 20, "c4": 20}
+        for name in ("c1", "c2", "c3", "c4"):
+            res, _bufs = bench_config(name, plan_steps[name], 3, 1 if name == "c3" else 3)
+            del _bufs
+            torch.cuda.empty_cache()
+            per[name] = res
+        per.update(bench_moves())
+        torch.cuda.synchronize()
+        # the unmodified reference on the same problems (its own driver / MatrixMove over cuBLAS), same GPU, same run
+        for name in ("c1", "c2", "c3", "c4"):
+            ref = reference_run_tests(CONFIGS[name], 8, 3)
+            ours_ms = per[name].get("warm_l2", per[name])["ms_per_step"]
+            if ref and "best_ms" in ref:
+                per[name]["vs_reference"] = {"reference_ms": ref["best_ms"], "reference_plan": ref["best_plan"], "reference_tflops": ref["tflops"],
+                                             "ours_ms": ours_ms, "ratio": ref["best_ms"] / ours_ms,
+                                             "note": "oracle/_ref/run_tests (unmodified reference, cuBLAS 12.9), exhaustive over its plans, mean of 5 samples after 3; "
+                                                     "ours = planner steps back to back (warm L2 where the inputs fit, as the reference's harness measures)"}
+            else:
+                per[name]["vs_reference"] = ref
+        mv = reference_moves(20)
+        for name, *_ in MOVES:
+            r = mv.get(name)
+            if r:
+                per[name]["vs_reference"] = {"reference_gbs": r["median_gbs"], "reference_ms": r["median_ms"], "ours_gbs": per[name]["warm_l2_gbs"],
+                                             "ratio": per[name]["warm_l2_gbs"] / r["median_gbs"],
+                                             "note": "oracle/_ref/ref_driver time_move: the reference's MatrixMove over cublasDgeam, event pairs, median of 20, no L2 flush; "
+                                                     "ours under the same conditions (warm_l2_gbs)"}
+        line["per_config"] = per
 
     if rank == 0:
-        stats = planner.statistics() if world == 1 else [{"options": []}]
-        per_plan = {}
-        for o in stats[0]["options"]:
-            name = "".join(o["option"][x] for x in ("transA", "transB", "transC", "padA", "padB", "padC") if x in o["option"])
-            if o["times"]:
-                per_plan[name] = round(sorted(o["times"])[len(o["times"]) // 2], 4)  # median of the logged samples
-        if len(per_plan) > 8:  # 64-plan space: keep the line readable
-            per_plan = dict(sorted(per_plan.items(), key=lambda kv: kv[1])[:8])
-        line = {
-            "metric": "gemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-            "dtype": "f64" if dbl else "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg_name}: {dtype} GEMM op {ta_s}{tb_s} m={m} n={n} k={k} alpha=1 beta=0 through Planning_System (autotuned plan)",
-                       "plan": chosen, "plan_meaning": "NNN = transpose/pad fused into the GEMM's loads; T.. = explicit MatrixMove pass first",
-                       "best_ms_per_plan": per_plan,
-                       "parallelism": f"column split of C over {world} GPU(s)" + (f", A replicated every step from rank 0 by {transport}, 4 K-panels (1/16, 3/16, 4/16, 8/16 of K) pipelined with the GEMM" if world > 1 else ""),
-                       "l2_policy": "inputs larger than L2 (126 MB): no flush needed" if (ar * ac + br * bc) * esz > 200e6 else "inputs fit in L2; back-to-back steps measure the warm-L2 case the reference's harness also sees",
-                       "pct_of_fp64_dmma_peak": round(100 * value / (DMMA_PEAK_TFLOPS * world), 2) if dbl else None},
-            "roofline": roof, "gpu_launches": launches, "clocks": clocks, "kernel": kernel_name,
-        }
-        if e2e:
-            line["e2e"] = e2e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_baseline(cfg)
         print(json.dumps(line), flush=True)

@@ -11,7 +11,7 @@
  *   Planning_System::calculate_workspace (:116-118)              rtat_host_planner_workspace
  *   Planning_System::make_statistics + Planner_Statistics::json  rtat_host_planner_statistics
  *     (:120-130, src/planning/planner_statistics.h:50-67)
- *   (new) JSON plan cache                                        rtat_host_planner_{save,load}_plans
+ *   (new) JSON plan cache, in memory and on disk                 rtat_host_planner_{save,load}_plans[_file]
  *
  * Matrices are device pointers, column-major; the work runs on the stream bound to `handle`.
  * Functions returning char* hand out malloc'd text to be released with rtat_host_free.
@@ -58,6 +58,16 @@ char *rtat_host_planner_statistics(rtat_host_planner_t planner);
 char *rtat_host_planner_save_plans(rtat_host_planner_t planner);
 long long rtat_host_planner_load_plans(rtat_host_planner_t planner, const char *json_text);
 int rtat_host_planner_set_tests_until_converge(rtat_host_planner_t planner, int n);
+/* On-disk plan cache (reference src/app/runner.h:81-82 keeps its statistics in a JSON file the same way): save overwrites
+ * `path` with the converged plans; load returns how many plans were taken over (0 when the file does not exist), -1 when
+ * the file is malformed. */
+int rtat_host_planner_save_plans_file(rtat_host_planner_t planner, const char *path);
+long long rtat_host_planner_load_plans_file(rtat_host_planner_t planner, const char *path);
+/* Planning_System::set_default_preference: relative margin within which the default plan is kept over a faster-looking
+ * one (0, the default, = the reference's strict minimum of the means). */
+int rtat_host_planner_set_default_preference(rtat_host_planner_t planner, double margin);
+/* statistics with the derived columns "tflops" / "gbs" next to "times" (what run_tests prints) */
+char *rtat_host_planner_statistics_rates(rtat_host_planner_t planner);
 int rtat_host_planner_num_plans(rtat_host_planner_t planner);
 char *rtat_host_planner_plan_name(rtat_host_planner_t planner, int index);
 void rtat_host_free(char *text);

@@ -5,12 +5,17 @@
 //
 //   ref_driver golden <out.bin> <out.json>      run the fixed golden case list (needs a GPU)
 //   ref_driver golden_l3 <out.bin> <out.json>   SYRK / TRSM executors and raw calls (needs a GPU)
+//   ref_driver time_move <reps>                 time the reference's MatrixMove (cublas?geam) on bench.py's matrix_op
+//                                               shapes with event pairs; one JSON object on stdout (needs a GPU)
 //
 // Inputs use the same counter-based generator as oracle_fill_uniform_* / rtat_b200_fill_uniform_*
 // so the consumers regenerate them from (seed, count) instead of storing them.
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 #include <gemm.h>       // reference: src/methods/gemm.h
@@ -334,7 +339,56 @@ static void l3_cases(Sink &out, gpu::blasHandle_t handle, Stream s, uint64_t bas
         }
 }
 
+// MatrixMove (reference src/matrix_ops/matrixop.h:307-344) of an m x n source, timed like Executor::execute times a
+// plan (event pair on the handle's stream, reference src/methods/executor.h:18-33): best and median of `reps` runs.
+template <typename T>
+static void time_move_case(gpu::blasHandle_t handle, Stream s, const char *name, size_t m, size_t n, bool transpose, size_t pad,
+                           int reps, bool last) {
+  ManagedWorkspace src(m * n * sizeof(T) + 16);
+  gpuAssert(gpu::Memset(src, 0x3c, m * n * sizeof(T)));
+  Matrix<T> A(src, m, n, m);
+  std::unique_ptr<MatrixOp<T>> leaf = std::make_unique<NoOp<T>>(A);
+  MatrixMove<T> move(std::move(leaf), (T)1, transpose, pad);
+  const size_t out_bytes = move.output_space_req() * sizeof(T);
+  ManagedWorkspace dst(out_bytes + 16);
+  Workspace out((char *)dst, out_bytes), none((char *)dst + out_bytes, 0);
+  std::vector<float> ms;
+  for (int r = 0; r < reps + 3; r++) {
+    Event a, b;
+    a.record(s);
+    move.execute(handle, out, none);
+    b.record(s);
+    s.synchronize();
+    if (r >= 3) ms.push_back(Event::elapsed_time(a, b));
+  }
+  std::sort(ms.begin(), ms.end());
+  const double bytes = 2.0 * m * n * sizeof(T);
+  printf("  \"%s\": {\"rows\": %zu, \"cols\": %zu, \"transpose\": %d, \"ld_out\": %zu, \"bytes\": %.0f, \"best_ms\": %.6f, \"median_ms\": %.6f, "
+         "\"best_gbs\": %.1f, \"median_gbs\": %.1f}%s\n",
+         name, m, n, (int)transpose, move.dims().ld, bytes, ms.front(), ms[ms.size() / 2], bytes / ms.front() * 1e-6, bytes / ms[ms.size() / 2] * 1e-6,
+         last ? "" : ",");
+}
+
+static int time_move_main(int reps) {
+  Stream s;
+  gpu::blasHandle_t handle;
+  gpu::blasCreate(&handle);
+  gpu::blasSetStream(handle, s);
+  printf("{\n");
+  time_move_case<double>(handle, s, "transpose_8192_f64", 8192, 8192, true, 1, reps, false);
+  time_move_case<double>(handle, s, "copy_8192_f64", 8192, 8192, false, 1, reps, false);
+  time_move_case<double>(handle, s, "pad_copy_c3_A", 4097, 2049, false, 32, reps, false);   // config 3: A 4097 x 2049 -> ld 4128
+  time_move_case<double>(handle, s, "pad_copy_c3_B", 3001, 2049, false, 32, reps, false);   // config 3: B 3001 x 2049 -> ld 3008
+  time_move_case<double>(handle, s, "transpose_pad_c3_A", 4097, 2049, true, 32, reps, false);  // -> 2049 x 4097, ld 2080
+  time_move_case<double>(handle, s, "transpose_c3_A_tight", 4097, 2049, true, 1, reps, false); // -> ld 2049 (odd target)
+  time_move_case<float>(handle, s, "transpose_131072x128_f32", 131072, 128, true, 1, reps, true);
+  printf("}\n");
+  gpu::blasDestroy(handle);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc == 3 && std::string(argv[1]) == "time_move") return time_move_main(atoi(argv[2]) > 0 ? atoi(argv[2]) : 20);
   if (argc != 4 || (std::string(argv[1]) != "golden" && std::string(argv[1]) != "golden_l3")) {
     fprintf(stderr, "usage: ref_driver golden|golden_l3 <out.bin> <out.json>\n");
     return 2;

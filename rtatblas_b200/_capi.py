@@ -13,7 +13,8 @@ class RtatError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "librtat_b200.so")
+    # RTAT_B200_LIB: an experiment build of the same library (probe/build_variants.sh); never a different back end
+    return os.environ.get("RTAT_B200_LIB") or os.path.join(_HERE, "lib", "librtat_b200.so")
 
 
 _lib = None

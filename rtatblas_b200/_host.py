@@ -39,6 +39,12 @@ def host_lib():
         L.rtat_host_planner_load_plans.restype = ll
         L.rtat_host_planner_load_plans.argtypes = [vp, cp]
         L.rtat_host_planner_set_tests_until_converge.argtypes = [vp, i]
+        L.rtat_host_planner_save_plans_file.argtypes = [vp, cp]
+        L.rtat_host_planner_load_plans_file.restype = ll
+        L.rtat_host_planner_load_plans_file.argtypes = [vp, cp]
+        L.rtat_host_planner_set_default_preference.argtypes = [vp, C.c_double]
+        L.rtat_host_planner_statistics_rates.restype = vp
+        L.rtat_host_planner_statistics_rates.argtypes = [vp]
         L.rtat_host_planner_num_plans.argtypes = [vp]
         L.rtat_host_planner_plan_name.restype = vp
         L.rtat_host_planner_plan_name.argtypes = [vp, i]
@@ -150,3 +156,21 @@ class Planner:
 
     def set_tests_until_converge(self, n):
         host_lib().rtat_host_planner_set_tests_until_converge(self._p, n)
+
+    def set_default_preference(self, margin):
+        """keep the default (fused) plan unless another one is faster by more than `margin` (0 = the reference's strict minimum)"""
+        host_lib().rtat_host_planner_set_default_preference(self._p, float(margin))
+
+    def save_plans_file(self, path):
+        if host_lib().rtat_host_planner_save_plans_file(self._p, str(path).encode()) != 0:
+            raise RtatError(host_lib().rtat_host_last_error().decode())
+
+    def load_plans_file(self, path):
+        r = host_lib().rtat_host_planner_load_plans_file(self._p, str(path).encode())
+        if r < 0:
+            raise RtatError(host_lib().rtat_host_last_error().decode())
+        return r
+
+    def statistics_rates(self):
+        """statistics() plus per-sample "tflops" (and "gbs" for GEMM keys) beside every plan's "times" list"""
+        return json.loads(_take(host_lib().rtat_host_planner_statistics_rates(self._p)))

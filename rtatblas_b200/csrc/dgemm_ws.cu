@@ -33,6 +33,16 @@ namespace rtat_b200 {
 
 namespace ws {
 
+// experiment switches (probe/build_variants.sh); the defaults are the shipped configuration
+#ifndef RTAT_WS_FENCE_ARRIVE
+#define RTAT_WS_FENCE_ARRIVE 0
+#endif
+#ifndef RTAT_WS_FENCE_WAIT
+#define RTAT_WS_FENCE_WAIT 0
+#endif
+#ifndef RTAT_WS_CTAS64
+#define RTAT_WS_CTAS64 2
+#endif
 constexpr int BK = 16;
 constexpr int CPASYNC_PRODUCER_WARPS = 4;
 
@@ -51,12 +61,18 @@ struct TileCfg {
   static constexpr bool FINE_EDGES = BM_ == 64;
   // 128x128 tiles: the consumers need more registers than an even split of the file gives them (setmaxnreg, see the
   // kernel); 64x64 tiles hold 64 accumulator registers and do not
-  static constexpr bool SPLIT_REGS = BM_ == 128;
+#ifndef RTAT_WS_SPLIT64
+#define RTAT_WS_SPLIT64 0
+#endif
+  static constexpr bool SPLIT_REGS = BM_ == 128 || RTAT_WS_SPLIT64;
   // 16-byte fragment loads + permuted k (see kmap) or the original 8-byte scheme (see FragAddr64)
-  static constexpr bool VEC_FRAGS = BM_ == 128;
+#ifndef RTAT_WS_VEC64
+#define RTAT_WS_VEC64 0
+#endif
+  static constexpr bool VEC_FRAGS = BM_ == 128 || RTAT_WS_VEC64;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
-using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
+using Cfg64 = TileCfg<64, 64, 32, 32, 6, RTAT_WS_CTAS64>;
 
 struct Params {
   int m, n, k;
@@ -425,10 +441,23 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   // (128x128 tiles; SPLIT_REGS), so what the producers give back — a TMA issuer needs next to nothing — lets the
   // consumers hold 128 accumulator registers plus a whole half k-tile of fragments without spilling.  The producer
   // warpgroup is always four warps (three of them idle with TMA) because the instruction is warpgroup-wide.
+  // Budget: the kernel launches with LAUNCH_REGS per thread (what __launch_bounds__ leaves each of the CTAS_PER_SM
+  // resident CTAs); the four producer warps shrink to PRODUCER_REGS and the consumers share what that frees.
   constexpr int PRODUCER_REGS = USE_TMA ? 40 : 56;
-  constexpr int CONSUMER_REGS = ((512 - PRODUCER_REGS) / 2 / 8) * 8;
+  constexpr int LAUNCH_REGS = 65536 / ((CONSUMER_WARPS + CPASYNC_PRODUCER_WARPS) * 32 * Cfg::CTAS_PER_SM) / 8 * 8;
+  constexpr int CONSUMER_REGS = (LAUNCH_REGS + (LAUNCH_REGS - PRODUCER_REGS) * CPASYNC_PRODUCER_WARPS / CONSUMER_WARPS) / 8 * 8;
+  static_assert(!Cfg::SPLIT_REGS || BM != 128 || CONSUMER_REGS == 232 || CONSUMER_REGS == 224, "128x128 split as measured");
+#ifndef RTAT_WS_PARK
+#define RTAT_WS_PARK 0
+#endif
+  constexpr int PARK_THREADS = (CONSUMER_WARPS + CPASYNC_PRODUCER_WARPS - 1) * 32;  // consumers + the idle producer warps
   if (warp >= CONSUMER_WARPS) {
     if (Cfg::SPLIT_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PRODUCER_REGS));
+    if (RTAT_WS_PARK && Cfg::SPLIT_REGS && USE_TMA && warp > CONSUMER_WARPS) {
+      // experiment: the idle warps of the producer warpgroup stay resident until the consumers are done
+      asm volatile("bar.sync 2, %0;\n" ::"n"(PARK_THREADS) : "memory");
+      return;
+    }
     // ======================= producer =======================
     int stage = 0;
     uint32_t phase = 0;
@@ -536,6 +565,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const bool active = whole || (mi_act > 0 && ni_act > 0);
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
+        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         if (active) {
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll
@@ -551,6 +581,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[e][i], fb[e][j]);
           }
         }
+        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -559,6 +590,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
+        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         const uint32_t sbase = smem_base + stage * STAGE_BYTES;
         if (mi_act > 0 && ni_act > 0) {
 #pragma unroll
@@ -577,6 +609,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
           }
         }
+        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -589,6 +622,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const bool active = whole || (mi_act > 0 && ni_act > 0);
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
+        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         if (active) {
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           double fa[2][MI], fb[2][NI];
@@ -611,6 +645,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[cur][i], fb[cur][j]);
           }
         }
+        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -619,6 +654,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
+        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         const uint32_t sbase = smem_base + stage * STAGE_BYTES;
         if (mi_act > 0 && ni_act > 0) {
 #pragma unroll
@@ -639,6 +675,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               }
           }
         }
+        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -720,6 +757,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   }
+  if (RTAT_WS_PARK && Cfg::SPLIT_REGS && USE_TMA) asm volatile("bar.arrive 2, %0;\n" ::"n"(PARK_THREADS) : "memory");
 }
 
 // ---- host side ---------------------------------------------------------------------------------------

@@ -43,7 +43,11 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
     blocks++;
   }
   int panels = 1, lead = 0;
-  if (blocks > 1 && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
+  // The multi-GPU entry is collective: every rank must cut K into the SAME panels (the peers' "panel p has arrived" flags
+  // are indexed by p), so for that caller the decision may depend only on what the collective contract fixes — m, k, lda,
+  // transa (through bytes_a) and the world size — never on this rank's n_loc.  The single-GPU caller keeps the
+  // "a single column block cannot be pipelined" shortcut.
+  if ((multi || blocks > 1) && k >= 2048 && bytes_a >= (size_t(32) << 20)) {
     panels = k / 1024 < MAX_PANELS ? k / 1024 : MAX_PANELS;
     const double rate = elem == 8 ? 33e12 : 150e12;  // nominal: only the split point depends on them
     const double t_a = double(bytes_a) * a_share / pcie_rate, t_b = double(elem) * k * nb / pcie_rate, t_mm = 2.0 * m * nb * double(k) / rate;

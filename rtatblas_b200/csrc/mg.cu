@@ -15,6 +15,17 @@ struct rtat_b200_mg_context {
   std::vector<cudaEvent_t> landed;    // panel p has arrived in A_stage
   std::vector<cudaEvent_t> consumed;  // panel p of the previous call has been read by its GEMM
   bool consumed_valid = false;
+  // What the previous rtat_b200_mg_dgemm call staged where: the per-panel `consumed` events order the reuse of A_stage only
+  // when this call cuts the same bytes into the same panels; any other call waits for ALL of the previous call's GEMMs.
+  struct StageSignature {
+    const void *stage = nullptr;
+    int transa = -1, m = 0, k = 0, lda = 0, panels = 0;
+    bool auto_schedule = false;
+    bool operator==(const StageSignature &o) const {
+      return stage == o.stage && transa == o.transa && m == o.m && k == o.k && lda == o.lda && panels == o.panels && auto_schedule == o.auto_schedule;
+    }
+  } last_signature;
+  cudaEvent_t last_consumed = nullptr;  // recorded on the math stream after the previous call's last GEMM
   // ---- host-buffer entry (rtat_b200_mg_dgemm_host): every rank owns a replica of A in IPC-exportable memory, preceded by
   // a flag page that the peers write into
   char *replica = nullptr;                       // own allocation: [flag page][A]
@@ -42,6 +53,8 @@ constexpr size_t GEN_WORD = 1024 + 65;  // this rank's current generation, the s
 __global__ void mg_wait_kernel(const unsigned *flag, unsigned value, unsigned *status) {
   unsigned long long t0, now;
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+  // one timed-out wait fails the call: the waits queued behind it give up at once instead of each spending its own 30 s
+  if (*reinterpret_cast<volatile unsigned *>(status)) return;
   for (;;) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
@@ -140,6 +153,7 @@ int rtat_b200_mg_destroy(rtat_b200_mg_t mg) {
   cudaStreamSynchronize(mg->copy_stream);
   for (auto e : mg->landed) cudaEventDestroy(e);
   for (auto e : mg->consumed) cudaEventDestroy(e);
+  if (mg->last_consumed) cudaEventDestroy(mg->last_consumed);
   cudaStreamDestroy(mg->copy_stream);
   rtat_b200_mg_host_teardown(mg);
   delete mg;
@@ -191,6 +205,15 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
                        int lda, double *A_stage, const double *B_loc, int ldb, const double *beta, double *C_loc, int ldc, int panels) {
   if (!mg || !alpha || !beta) return RTAT_B200_STATUS_INVALID_VALUE;
   if (panels < 0) return RTAT_B200_STATUS_INVALID_VALUE;
+  // validated here, before the first panel copy is queued (the GEMM entry would only catch it after the copy engine had
+  // been told to move lda * k elements)
+  if ((transa != RTAT_B200_OP_N && transa != RTAT_B200_OP_T) || (transb != RTAT_B200_OP_N && transb != RTAT_B200_OP_T) || m < 0 || n_loc < 0 ||
+      k < 0)
+    return RTAT_B200_STATUS_INVALID_VALUE;
+  {
+    const int rows_a = transa == RTAT_B200_OP_N ? m : k, rows_b = transb == RTAT_B200_OP_N ? k : n_loc;
+    if (lda < (rows_a > 1 ? rows_a : 1) || ldb < (rows_b > 1 ? rows_b : 1) || ldc < (m > 1 ? m : 1)) return RTAT_B200_STATUS_INVALID_VALUE;
+  }
   const bool auto_schedule = panels == 0;
   if (auto_schedule) panels = 4;
   rtat_b200_context *h = mg->h;
@@ -202,6 +225,18 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
   const double one = 1.0;
   const bool ta = transa == RTAT_B200_OP_T, tb = transb == RTAT_B200_OP_T;
   bool first_gemm = true;
+  // Reuse of A_stage: with the schedule of the previous call, panel p may be overwritten as soon as ITS previous GEMM is done
+  // (so the next step's first panel streams in under this step's last GEMMs); with any other schedule a new panel can cover
+  // bytes that a different, later panel of the previous call is still being read from, so the copy stream waits for all of it.
+  rtat_b200_mg_context::StageSignature sig;
+  sig.stage = A_stage; sig.transa = transa; sig.m = m; sig.k = k; sig.lda = lda; sig.panels = panels; sig.auto_schedule = auto_schedule;
+  const bool same_schedule = mg->consumed_valid && sig == mg->last_signature;
+  if (mg->consumed_valid && !same_schedule) {
+    if (cudaStreamWaitEvent(mg->copy_stream, mg->last_consumed, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return RTAT_B200_STATUS_EXECUTION_FAILED;
+    }
+  }
   for (int p = 0; p < panels; p++) {
     int k0, kw;
     if (auto_schedule) rtat_b200_mg_auto_panel(k, p, &k0, &kw);
@@ -215,7 +250,7 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
       (void)cudaGetLastError();
       return false;
     };
-    if (mg->consumed_valid && !sync_ok(cudaStreamWaitEvent(mg->copy_stream, mg->consumed[p], 0), "wait for the slot"))
+    if (same_schedule && !sync_ok(cudaStreamWaitEvent(mg->copy_stream, mg->consumed[p], 0), "wait for the slot"))
       return RTAT_B200_STATUS_EXECUTION_FAILED;
     cudaError_t e;
     if (!ta) {
@@ -243,6 +278,15 @@ int rtat_b200_mg_dgemm(rtat_b200_mg_t mg, int transa, int transb, int m, int n_l
     if (st) return st;
     if (!sync_ok(cudaEventRecord(mg->consumed[p], h->stream), "record panel consumed")) return RTAT_B200_STATUS_EXECUTION_FAILED;
   }
+  if (!mg->last_consumed && cudaEventCreateWithFlags(&mg->last_consumed, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_ALLOC_FAILED;
+  }
+  if (cudaEventRecord(mg->last_consumed, h->stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RTAT_B200_STATUS_EXECUTION_FAILED;
+  }
+  mg->last_signature = sig;
   mg->consumed_valid = true;
   return RTAT_B200_STATUS_SUCCESS;
 }
@@ -442,8 +486,11 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
                     int lb, double be, double *c, int lc) { return rtat_b200::dgemm(hh, ta_, tb_, mm, nn, kk, al, a, la, b, lb, be, c, lc); };
   int st = rtat_b200::gemm_host_pipeline<double>(h, transa, transb, m, n_loc, k, alpha, A, lda, B_loc, ldb, beta, C_loc, ldc, gemm_fn, &hooks);
   if (W > 1) {
-    if (!started && !host_cuda_ok(cudaMemcpyAsync(my_flags + GEN_WORD, &mg->generation_pinned[0], sizeof(unsigned), cudaMemcpyHostToDevice,
-                                                  mg->pull_stream), "generation word"))
+    // pushed flags (mg.signal = 0) are device-to-device copies OF the generation word: (re)write it on the stream that is
+    // about to read it, so the read cannot overtake the upload that copy_in carried at the start of the call
+    if ((!started || signal_mode != 1) &&
+        !host_cuda_ok(cudaMemcpyAsync(my_flags + GEN_WORD, &mg->generation_pinned[0], sizeof(unsigned), cudaMemcpyHostToDevice,
+                                      mg->pull_stream), "generation word"))
       return RTAT_B200_STATUS_EXECUTION_FAILED;
     // tell every peer that this rank no longer reads their replicas of this generation (all pulls are behind us on pull_stream)
     if (!signal_peers(mg->pull_stream, done_word(R))) return RTAT_B200_STATUS_EXECUTION_FAILED;
@@ -453,6 +500,8 @@ int rtat_b200_mg_dgemm_host(rtat_b200_mg_t mg, int transa, int transb, int m, in
         !host_cuda_ok(cudaMemcpy(&status, my_flags + STATUS_WORD, sizeof status, cudaMemcpyDeviceToHost), "read status"))
       return RTAT_B200_STATUS_EXECUTION_FAILED;
     if (status) {
+      // report once: the word is cleared so that a later, healthy call on this context is not failed by this one
+      (void)cudaMemset(my_flags + STATUS_WORD, 0, sizeof(unsigned));
       fprintf(stderr, "rtat_b200_mg: rank %d timed out waiting for a peer's share of A (is every rank making this call?)\n", R);
       return RTAT_B200_STATUS_EXECUTION_FAILED;
     }

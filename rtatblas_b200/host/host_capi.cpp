@@ -31,6 +31,10 @@ struct Planner_Base {
   virtual std::string save_plans() = 0;
   virtual long long load_plans(const char *text) = 0;
   virtual void set_converge(int n) = 0;
+  virtual void set_preference(double margin) = 0;
+  virtual void save_plans_file(const char *path) = 0;
+  virtual long long load_plans_file(const char *path) = 0;
+  virtual std::string statistics_rates() = 0;
   virtual int num_plans() = 0;
   virtual std::string plan_name(int i) = 0;
 };
@@ -64,6 +68,10 @@ struct Planner_Common : Planner_Base {
   std::string save_plans() override { return planner.save_plans().dump(1); }
   long long load_plans(const char *text) override { return (long long)planner.load_plans(Json::parse(text)); }
   void set_converge(int n) override { planner.set_tests_until_converge((size_t)n); }
+  void set_preference(double margin) override { planner.set_default_preference((float)margin); }
+  void save_plans_file(const char *path) override { planner.save_plans_file(path); }
+  long long load_plans_file(const char *path) override { return (long long)planner.load_plans_file(path); }
+  std::string statistics_rates() override { return planner.make_statistics().json(sizeof(typename Exec::Params_T::Scalar)).dump(1); }
   int num_plans() override { return (int)Opts::enumerate().size(); }
   std::string plan_name(int i) override { return std::string(Opts::enumerate().at((size_t)i)); }
 };
@@ -243,6 +251,25 @@ int rtat_host_planner_set_tests_until_converge(rtat_host_planner_t p, int n) {
   if (!p) return -1;
   static_cast<Planner_Base *>(p)->set_converge(n);
   return 0;
+}
+int rtat_host_planner_save_plans_file(rtat_host_planner_t p, const char *path) {
+  if (!p || !path) return -1;
+  return guarded([&] { static_cast<Planner_Base *>(p)->save_plans_file(path); return 0; });
+}
+long long rtat_host_planner_load_plans_file(rtat_host_planner_t p, const char *path) {
+  long long out = -1;
+  if (p && path) guarded([&] { out = static_cast<Planner_Base *>(p)->load_plans_file(path); return 0; });
+  return out;
+}
+int rtat_host_planner_set_default_preference(rtat_host_planner_t p, double margin) {
+  if (!p) return -1;
+  static_cast<Planner_Base *>(p)->set_preference(margin);
+  return 0;
+}
+char *rtat_host_planner_statistics_rates(rtat_host_planner_t p) {
+  char *out = nullptr;
+  if (p) guarded([&] { out = dup_string(static_cast<Planner_Base *>(p)->statistics_rates()); return 0; });
+  return out;
 }
 int rtat_host_planner_num_plans(rtat_host_planner_t p) { return p ? static_cast<Planner_Base *>(p)->num_plans() : -1; }
 char *rtat_host_planner_plan_name(rtat_host_planner_t p, int i) {

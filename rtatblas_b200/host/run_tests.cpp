@@ -1,6 +1,7 @@
 // run_tests <input.json> — the reference's benchmark driver (src/app/run_tests.cpp) on the B200
 // back end: reads a problem list, runs it exhaustively or through the auto-tuner, prints the input
-// document with "problems" replaced by per-plan event times (ms).
+// document with "problems" replaced by per-plan event times (ms) and the TFLOP/s / GB/s they amount to; keyword
+// "plan_cache" keeps the converged plans in a file across runs (see test_harness.h).
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -10,12 +11,14 @@ using namespace rtat;
 
 template <typename Executor>
 static Json run(const Input_File &file) {
-  Test_Harness<Planning_System<Executor>> harness(file.problem_json, (uint64_t)file.seed);
+  Test_Harness<Planning_System<Executor>> harness(file.problem_json, (uint64_t)file.seed, file.plan_cache, file.rates);
   return file.run_type.val == Run_Type::EXHAUSTIVE ? harness.run_exhaustive(file.repetitions) : harness.run_autotune(file.repetitions);
 }
 
 static Json dispatch(const Input_File &file) {
   const bool dbl = file.data_type.val == Data_Type::DOUBLE;
+  if (file.method.val == Method::MOVE)
+    return dbl ? run_moves<double>(file.problem_json, file.repetitions, (uint64_t)file.seed) : run_moves<float>(file.problem_json, file.repetitions, (uint64_t)file.seed);
   if (file.method.val == Method::TRSM) return dbl ? run<TRSM_Executor<double>>(file) : run<TRSM_Executor<float>>(file);
   if (file.method.val == Method::SYRK) return dbl ? run<SYRK_Executor<double>>(file) : run<SYRK_Executor<float>>(file);
   if (file.method.val == Method::GEMM) return dbl ? run<GEMM_Executor<double>>(file) : run<GEMM_Executor<float>>(file);

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <iostream>
 #include <memory>
+#include <vector>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -132,14 +133,49 @@ class Stream {
   void synchronize() { gpuAssert(gpu::StreamSynchronize(*this)); }
 };
 
+namespace detail {
+// Every timed execute needs two events (reference src/methods/executor.h:18-33); creating and destroying them per call
+// costs more host time than launching a small GEMM, so released events go back to a per-thread, per-device free list.
+// The lists are deliberately never torn down: the driver reclaims the events with the context.
+struct Event_Pool {
+  std::vector<std::vector<gpu::Event_t>> free_by_device;
+  static Event_Pool &get() {
+    static thread_local Event_Pool *pool = new Event_Pool;
+    return *pool;
+  }
+  static std::vector<gpu::Event_t> &list_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    auto &lists = get().free_by_device;
+    if ((int)lists.size() <= dev) lists.resize(dev + 1);
+    return lists[dev];
+  }
+};
+}  // namespace detail
+
 class Event {
   std::shared_ptr<CUevent_st> impl;
 
  public:
   Event() {
+    auto &free_list = detail::Event_Pool::list_for_current_device();
     gpu::Event_t e = nullptr;
-    gpuAssert(gpu::EventCreate(&e));
-    impl = std::shared_ptr<CUevent_st>(e, [](gpu::Event_t p) { if (p) gpuAssert(gpu::EventDestroy(p)); });
+    if (!free_list.empty()) {
+      e = free_list.back();
+      free_list.pop_back();
+    } else {
+      gpuAssert(gpu::EventCreate(&e));
+    }
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    // the deleter files the event under the device it was created on, in the pool of whichever thread drops the last reference
+    impl = std::shared_ptr<CUevent_st>(e, [dev](gpu::Event_t p) {
+      if (!p) return;
+      auto &lists = detail::Event_Pool::get().free_by_device;
+      if ((int)lists.size() <= dev) lists.resize(dev + 1);
+      if (lists[dev].size() < 4096) lists[dev].push_back(p);
+      else gpuAssert(gpu::EventDestroy(p));
+    });
   }
   Event(gpu::Event_t borrowed) : impl(borrowed, [](gpu::Event_t) {}) {}
   operator gpu::Event_t() const { return impl.get(); }

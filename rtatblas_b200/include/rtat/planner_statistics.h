@@ -6,10 +6,19 @@
 #include <algorithm>
 #include <map>
 #include <numeric>
+#include <type_traits>
+#include <utility>
 #include <vector>
 #include "json_encoding.h"
 
 namespace rtat {
+
+namespace detail {
+template <typename Key, typename = void>
+struct has_bytecount : std::false_type {};
+template <typename Key>
+struct has_bytecount<Key, std::void_t<decltype(std::declval<const Key &>().bytecount(size_t(8)))>> : std::true_type {};
+}  // namespace detail
 
 template <typename Key, typename Opts>
 class Planner_Statistics {
@@ -56,16 +65,29 @@ class Planner_Statistics {
     return best;
   }
 
-  Json json() const {
-    Json out = Json::array();
+  // `elem_bytes` > 0 adds two derived columns per plan next to "times": "tflops" (Key::flopcount / time, what the
+  // reference's get_floprates was meant to give, planner_statistics.h:35-48) and, for keys that define bytecount,
+  // "gbs" (algorithmic bytes of the call / time).  Like nlohmann's default-constructed values in the reference, an empty
+  // table prints as null and a key without plans gets "options": null.
+  Json json(size_t elem_bytes = 0) const {
+    Json out = times.empty() ? Json() : Json::array();
     for (auto &[key, per_plan] : times) {
       Json entry = Json::object();
       entry["key"] = to_json(key);
-      Json plans = Json::array();
+      Json plans = per_plan.empty() ? Json() : Json::array();
       for (auto &[opt, ts] : per_plan) {
         Json p = Json::object();
         p["option"] = to_json(opt);
         p["times"] = Json(ts);
+        if (elem_bytes > 0) {
+          std::vector<double> tf, gb;
+          for (float ms : ts) {
+            tf.push_back(key.flopcount() / (double(ms) * 1e-3) * 1e-12);
+            if constexpr (detail::has_bytecount<Key>::value) gb.push_back(key.bytecount(elem_bytes) / (double(ms) * 1e-3) * 1e-9);
+          }
+          p["tflops"] = Json(tf);
+          if constexpr (detail::has_bytecount<Key>::value) p["gbs"] = Json(gb);
+        }
         plans.push_back(p);
       }
       entry["options"] = plans;

@@ -5,9 +5,13 @@
 // New here: the converged choices can be saved to / pre-seeded from a JSON plan cache, so a
 // process does not have to re-explore shapes a previous run already tuned.
 #pragma once
+#include <fstream>
 #include <limits>
 #include <map>
 #include <numeric>
+#include <sstream>
+#include <stdexcept>
+#include <string>
 #include <utility>
 #include "gemm.h"
 #include "gpu-api.h"
@@ -44,7 +48,9 @@ class Planning_System {
   Executor_Type executor;
   const Option_Filter<Key, Opts> opt_filter;
   size_t tests_until_converge = 1;
-  float default_preference = 0.02f;  // relative margin within which the default plan is kept (0 = strict minimum)
+  // relative margin within which the default plan is kept over a faster-looking one; 0 = the reference's strict minimum
+  // of the means (planning_system.h:84-95).  Drivers that sample short problems opt in with set_default_preference.
+  float default_preference = 0.f;
   std::map<Key, Opts> converged_plans;
   Device_Timer::Mode sync_mode = Device_Timer::ASYNCHRONOUS;
 
@@ -74,8 +80,8 @@ class Planning_System {
       const float mean = float(std::accumulate(ts.begin(), ts.end(), 0.0) / ts.size());
       if (mean < best_ms) { best = opts; best_ms = mean; }
     }
-    // Event timings of short problems jitter by a few per cent; a plan that spends extra passes and workspace must win
-    // by more than that to displace the default (fully fused) plan.  The reference takes the strict minimum.
+    // Optional (off by default): event timings of short problems jitter by a few per cent; with a margin set, a plan that
+    // spends extra passes and workspace must win by more than that to displace the default (fully fused) plan.
     if (default_preference > 0.f) {
       const Opts dflt = Opts::default_opts();
       auto it = timings.find(dflt);
@@ -126,6 +132,20 @@ class Planning_System {
       out.push_back(e);
     }
     return out;
+  }
+  // On-disk form of the same cache (reference src/app/runner.h:81-82 writes its statistics the same way: one JSON
+  // document per file).  save: overwrite `path`; load: missing file = empty cache (0), malformed file throws.
+  void save_plans_file(const std::string &path) const {
+    std::ofstream out(path, std::ios::trunc);
+    if (!out) throw std::runtime_error("plan cache: cannot write " + path);
+    out << save_plans().dump(1) << "\n";
+  }
+  size_t load_plans_file(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) return 0;
+    std::stringstream text;
+    text << in.rdbuf();
+    return load_plans(Json::parse(text.str()));
   }
   // returns the number of plans taken over; entries whose plan the filter rejects are skipped
   size_t load_plans(const Json &cache) {

@@ -1,6 +1,9 @@
 // Host-only tests of the C++ layer (no GPU needed): restated from the reference's
 // tests/workspace_test.cpp and tests/json_test.cpp, plus the plan algebra / key ordering /
 // option enumeration / op-tree workspace accounting that the reference only exercises on a GPU.
+#include <unistd.h>
+#include <cstdlib>
+#include <fstream>
 #include <set>
 #include <sstream>
 #include <rtat/rtat.h>
@@ -346,6 +349,61 @@ TEST(Facade_Test, Lazy_Planners) {
   GEMM_Key key(gpu::BLAS_OP_T, gpu::BLAS_OP_N, 8192, 8192, 8192);
   ASSERT_EQ(std::string(d1.create_plan(key)), std::string("NNN"));  // served from the cache, no exploration
   ASSERT_EQ(d1.save_plans(), cache);
+}
+
+// The plan cache on disk (reference src/app/runner.h:81-82 keeps its planner output in a JSON file): what one process
+// tuned, the next one loads, creates plans from without exploring, and writes back unchanged.
+TEST(Plan_Cache_Test, File_Round_Trip) {
+  char path[] = "/tmp/rtat_plan_cache_XXXXXX";
+  int fd = mkstemp(path);
+  ASSERT_TRUE(fd >= 0);
+  close(fd);
+  std::remove(path);
+  GEMM_Key c2(gpu::BLAS_OP_T, gpu::BLAS_OP_N, 8192, 8192, 8192), c1(gpu::BLAS_OP_N, gpu::BLAS_OP_N, 1024, 1024, 1024);
+  {
+    GEMM_Planner first;
+    ASSERT_EQ(first.load_plans_file(path), 0u);  // a missing file is an empty cache
+    Json cache = Json::parse(
+        "[{\"key\": {\"transA\":\"T\",\"transB\":\"N\",\"m\":8192,\"n\":8192,\"k\":8192}, \"option\": {\"transA\":\"T\",\"transB\":\"N\",\"transC\":\"N\"}},"
+        " {\"key\": {\"transA\":\"N\",\"transB\":\"N\",\"m\":1024,\"n\":1024,\"k\":1024}, \"option\": {\"transA\":\"N\",\"transB\":\"N\",\"transC\":\"N\"}}]");
+    ASSERT_EQ(first.load_plans(cache), 2u);
+    first.save_plans_file(path);
+  }
+  GEMM_Planner second;
+  ASSERT_EQ(second.load_plans_file(path), 2u);
+  ASSERT_EQ(std::string(second.create_plan(c2)), std::string("TNN"));  // served from the file, no exploration
+  ASSERT_EQ(std::string(second.create_plan(c1)), std::string("NNN"));
+  second.save_plans_file(path);
+  GEMM_Planner third;
+  ASSERT_EQ(third.load_plans_file(path), 2u);
+  ASSERT_EQ(third.save_plans(), second.save_plans());
+  // a malformed file is an error, not an empty cache
+  { std::ofstream bad(path, std::ios::trunc); bad << "[{\"key\": "; }
+  bool threw = false;
+  try { third.load_plans_file(path); } catch (const std::exception &) { threw = true; }
+  ASSERT_TRUE(threw);
+  std::remove(path);
+}
+
+// Statistics with the derived columns run_tests prints: TFLOP/s from Key::flopcount, GB/s from Key::bytecount; and the
+// reference's null for an empty table / a key without plans (nlohmann default-constructed values, planner_statistics.h:50-67).
+TEST(Statistics_Test, Rates_And_Empty_Forms) {
+  using Stats = Planner_Statistics<GEMM_Key, GEMM_Options>;
+  ASSERT_EQ(Stats({}).json().dump(), std::string("null"));
+  std::map<GEMM_Key, std::map<GEMM_Options, std::vector<float>>> t;
+  GEMM_Key key(gpu::BLAS_OP_N, gpu::BLAS_OP_N, 1024, 1024, 1024);
+  t[key];
+  ASSERT_EQ(Stats(t).json()[size_t(0)]["options"].dump(), std::string("null"));
+  t[key][GEMM_Options()] = {0.5f, 1.0f};
+  Json j = Stats(t).json(sizeof(double));
+  const Json &plan = j[size_t(0)]["options"][size_t(0)];
+  ASSERT_EQ(plan["times"].size(), 2u);
+  ASSERT_NEAR(plan["tflops"][size_t(1)].get<double>(), 2.0 * 1024 * 1024 * 1024 / 1e-3 * 1e-12, 1e-9);
+  ASSERT_NEAR(plan["gbs"][size_t(0)].get<double>(), 3.0 * 1024 * 1024 * 8 / 0.5e-3 * 1e-9, 1e-6);
+  ASSERT_TRUE(!Stats(t).json()[size_t(0)]["options"][size_t(0)].contains("tflops"));  // plain form = the reference's schema
+  // the reference's default: strict minimum of the means unless a margin is asked for
+  auto rates = Stats(t).get_floprates();
+  ASSERT_EQ(rates.at(key).at(GEMM_Options()).size(), 2u);
 }
 
 int main(int argc, char **argv) { return mini::run_all(argc, argv); }

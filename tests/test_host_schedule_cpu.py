@@ -74,3 +74,19 @@ def test_overrides_and_bad_arguments():
         rt.host_schedule(2, 0, 10, 10, 10, 10)
     with pytest.raises(rt.RtatError):
         rt.host_schedule(8, 0, -1, 10, 10, 10)
+
+
+def test_multi_gpu_panels_do_not_depend_on_the_ranks_column_count():
+    """rtat_b200_mg_dgemm_host is collective and n_loc may differ by one column between ranks (n = 256 * world + 1 puts one
+    rank on either side of the one-block / two-block threshold): every rank must cut K into the same panels, because the
+    peers' arrival flags are indexed by panel."""
+    for world in (2, 4, 8):
+        for transa in (0, 1):
+            for m, k in [(8192, 8192), (4096, 2048), (32768, 32768), (8192, 2047), (1000, 3000)]:
+                lda = k if transa else m
+                seen = set()
+                for n_loc in (1, 200, 256, 257, 511, 512, 513, 1024, 4096):
+                    sc = rt.host_schedule(8, transa, m, n_loc, k, lda, world)
+                    seen.add(tuple(sc["panels"]))
+                    _check(sc, n_loc, k)
+                assert len(seen) == 1, f"world {world} transa {transa} m {m} k {k}: panel schedules differ across n_loc: {seen}"

@@ -77,7 +77,7 @@ if which in ("all", "dgemm"):
     dgemm_cfg("dgemm NN 2048^3", 0, 0, 2048, 2048, 2048)
     dgemm_cfg("C5/8-like NN 8192x1024x8192", 0, 0, 8192, 1024, 8192)
 if which == "geam_tune":
-    for t in range(3):
+    for t in range(7):
         h.set_option("geam.tune", t)
         print("tune", t, end=" ")
         geam_cfg("copy 8192^2 f64", 0, 8192, 8192)

@@ -33,16 +33,6 @@ namespace rtat_b200 {
 
 namespace ws {
 
-// experiment switches (probe/build_variants.sh); the defaults are the shipped configuration
-#ifndef RTAT_WS_FENCE_ARRIVE
-#define RTAT_WS_FENCE_ARRIVE 0
-#endif
-#ifndef RTAT_WS_FENCE_WAIT
-#define RTAT_WS_FENCE_WAIT 0
-#endif
-#ifndef RTAT_WS_CTAS64
-#define RTAT_WS_CTAS64 2
-#endif
 constexpr int BK = 16;
 constexpr int CPASYNC_PRODUCER_WARPS = 4;
 
@@ -60,19 +50,11 @@ struct TileCfg {
   // consumers of a ragged tile skip single DMMA blocks (64x64 tiles) or only whole warps (128x128: at the register cap)
   static constexpr bool FINE_EDGES = BM_ == 64;
   // 128x128 tiles: the consumers need more registers than an even split of the file gives them (setmaxnreg, see the
-  // kernel); 64x64 tiles hold 64 accumulator registers and do not
-#ifndef RTAT_WS_SPLIT64
-#define RTAT_WS_SPLIT64 0
-#endif
-  static constexpr bool SPLIT_REGS = BM_ == 128 || RTAT_WS_SPLIT64;
-  // 16-byte fragment loads + permuted k (see kmap) or the original 8-byte scheme (see FragAddr64)
-#ifndef RTAT_WS_VEC64
-#define RTAT_WS_VEC64 0
-#endif
-  static constexpr bool VEC_FRAGS = BM_ == 128 || RTAT_WS_VEC64;
+  // kernel); 64x64 tiles hold 64 accumulator registers and do not (measured with the split: 1-3 % slower)
+  static constexpr bool SPLIT_REGS = BM_ == 128;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
-using Cfg64 = TileCfg<64, 64, 32, 32, 6, RTAT_WS_CTAS64>;
+using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
 
 struct Params {
   int m, n, k;
@@ -161,6 +143,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+// A consumer warp hands a ring stage back with release_stage(): a CTA-scope fence, THEN the arrive on the stage's "empty"
+// barrier.  The fence is load-bearing.  ptxas schedules the arrive (SASS SYNCS.ARRIVE) directly behind the last LDS of the
+// k-tile — the DMMAs that consume that load are moved after it — and gives it no scoreboard wait on the load, and the
+// hardware does not order a shared-memory read against a later arrive either: when this warp's arrive is the last one the
+// stage is waiting for, the producer's refill can reach shared memory before the read does.  Found with 16-byte fragment
+// loads on 64x64 tiles, two CTAs per SM (4-14 % of 4096 x 1024 x 1024 runs took a fragment from the NEXT fill of the stage:
+// with A(i, k) = k / 16 the errors are +6 per k-value, always in the load issued last before the arrive); 0 failures in
+// 36 000 runs with the fence, any of membar.cta / fence.acq_rel.cta / fence.proxy.async, none with a fence after the
+// full-barrier wait instead.  The 8-byte scheme and the 128x128 configuration never showed it (0 in 80 000 runs) but have
+// the same instruction pattern, so every release goes through here.  Cost: not measurable (30.01 vs 30.01 ms on 8192^3).
+// (profiles/r02_stage_release_race.txt.)
+__device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane) {
+  asm volatile("fence.acq_rel.cta;\n" ::: "memory");
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(empty_bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -206,11 +204,6 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double lds64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
   return v;
 }
 
@@ -263,43 +256,6 @@ struct FragAddr {
   __device__ __forceinline__ uint32_t pair(int a, int b) const {
     if (KC) return base + a * 1024 + off[b];
     return base + a * (BK * 128) + (b & 1) * 128 + (b >> 1) * 1024 + off[b & 1];
-  }
-};
-
-// ---- 8-byte fragment loads (64x64 tiles) ------------------------------------------------------------------
-// The 64x64 configuration keeps the original scheme: one LDS.64 per DMMA operand, k = 4 ks + q.  (The 16-byte scheme
-// above produced a sporadic wrong A fragment in one lane of the TN 64x64 TMA kernel — 2 of 72 runs of the multi-GPU
-// host worker, always the same element, never with 128x128 tiles; the cause was not found within the round, so the
-// proven path stays where the register pressure does not call for the new one.)
-// M/N-contiguous operand: a pair of DMMA blocks (b = 0, 1) shares one 16-wide atom; lane index x of block b owns
-// element rho2(b, x) of the atom.
-__host__ __device__ constexpr int rho2(int b, int x) { return 4 * b + (x & 1) + 8 * ((x >> 1) & 1) + 2 * (x >> 2); }
-template <bool KC>
-__host__ __device__ constexpr int phys_index64(int blk, int x) {
-  return KC ? 8 * blk + rho(x) : 16 * (blk / 2) + rho2(blk & 1, x);
-}
-// Per-thread fragment addressing for one operand: addr(blk, ks) = base + imm(blk, ks) + off[sel(blk, ks)]
-template <bool KC>
-struct FragAddr64 {
-  uint32_t base;
-  uint32_t off[4];
-  __device__ __forceinline__ void init(uint32_t tile_base_warp /* byte offset of the warp's first row */, int q, int x) {
-    if (KC) {
-      int r = rho(x);
-      int t = (q >> 1) ^ r;
-      base = tile_base_warp + r * 128 + ((q & 1) << 3);
-#pragma unroll
-      for (int ks = 0; ks < 4; ks++) off[ks] = uint32_t(((2 * ks) ^ t) & 7) << 4;
-    } else {
-      int t = ((((x >> 1) & 1) << 2) + (x >> 2)) ^ q;
-      base = tile_base_warp + q * 128 + ((x & 1) << 3);
-#pragma unroll
-      for (int u = 0; u < 4; u++) off[u] = uint32_t(((2 * u) ^ t) & 7) << 4;
-    }
-  }
-  __device__ __forceinline__ uint32_t addr(int blk, int ks) const {
-    if (KC) return base + blk * 1024 + off[ks];
-    return base + (blk >> 1) * (BK * 128) + ks * 512 + off[(blk & 1) | ((ks & 1) << 1)];
   }
 };
 
@@ -447,17 +403,8 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int LAUNCH_REGS = 65536 / ((CONSUMER_WARPS + CPASYNC_PRODUCER_WARPS) * 32 * Cfg::CTAS_PER_SM) / 8 * 8;
   constexpr int CONSUMER_REGS = (LAUNCH_REGS + (LAUNCH_REGS - PRODUCER_REGS) * CPASYNC_PRODUCER_WARPS / CONSUMER_WARPS) / 8 * 8;
   static_assert(!Cfg::SPLIT_REGS || BM != 128 || CONSUMER_REGS == 232 || CONSUMER_REGS == 224, "128x128 split as measured");
-#ifndef RTAT_WS_PARK
-#define RTAT_WS_PARK 0
-#endif
-  constexpr int PARK_THREADS = (CONSUMER_WARPS + CPASYNC_PRODUCER_WARPS - 1) * 32;  // consumers + the idle producer warps
   if (warp >= CONSUMER_WARPS) {
     if (Cfg::SPLIT_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PRODUCER_REGS));
-    if (RTAT_WS_PARK && Cfg::SPLIT_REGS && USE_TMA && warp > CONSUMER_WARPS) {
-      // experiment: the idle warps of the producer warpgroup stay resident until the consumers are done
-      asm volatile("bar.sync 2, %0;\n" ::"n"(PARK_THREADS) : "memory");
-      return;
-    }
     // ======================= producer =======================
     int stage = 0;
     uint32_t phase = 0;
@@ -520,21 +467,13 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int MI = WM / 8, NI = WN / 8, KS = BK / 4;
   const int q = lane % 4, g = lane / 4;
   const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
-  constexpr bool VEC = Cfg::VEC_FRAGS;
   FragAddr<KCA> fa_addr;
   FragAddr<KCB> fb_addr;
-  FragAddr64<KCA> fa64;
-  FragAddr64<KCB> fb64;
-  if (VEC) {
-    fa_addr.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
-    fb_addr.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
-  } else {
-    fa64.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
-    fb64.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
-  }
-  // physical index (within the warp tile) of DMMA block blk, lane index x, under the scheme in use
-  auto row_of = [](int blk, int x) { return VEC ? phys_index<KCA>(blk, x) : phys_index64<KCA>(blk, x); };
-  auto col_of = [](int blk, int x) { return VEC ? phys_index<KCB>(blk, x) : phys_index64<KCB>(blk, x); };
+  fa_addr.init(KCA ? wm0 * 128 : (wm0 / 16) * (BK * 128), q, g);
+  fb_addr.init(A_BYTES + (KCB ? wn0 * 128 : (wn0 / 16) * (BK * 128)), q, g);
+  // physical index (within the warp tile) of DMMA block blk, lane index x
+  auto row_of = [](int blk, int x) { return phys_index<KCA>(blk, x); };
+  auto col_of = [](int blk, int x) { return phys_index<KCB>(blk, x); };
 
   int stage = 0;
   uint32_t phase = 0;
@@ -558,14 +497,12 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int rv = min(max(p.m - m0 - wm0, 0), WM), cv = min(max(p.n - n0 - wn0, 0), WN);
     const int mi_act = KCA ? (rv + 7) / 8 : 2 * ((rv + 15) / 16), ni_act = KCB ? (cv + 7) / 8 : 2 * ((cv + 15) / 16);
     const bool whole = mi_act == MI && ni_act == NI;
-    if (VEC) {
     static_assert(KS == 4, "two halves of two DMMA steps per k-tile");
     if (whole || !Cfg::FINE_EDGES) {
       // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
       const bool active = whole || (mi_act > 0 && ni_act > 0);
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
-        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         if (active) {
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll
@@ -581,16 +518,13 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[e][i], fb[e][j]);
           }
         }
-        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        release_stage(bar_base + 8 * (STAGES + stage), lane);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     } else {
       // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
-        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
         const uint32_t sbase = smem_base + stage * STAGE_BYTES;
         if (mi_act > 0 && ni_act > 0) {
 #pragma unroll
@@ -609,80 +543,11 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
           }
         }
-        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        release_stage(bar_base + 8 * (STAGES + stage), lane);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
 
-    } else {
-    if (whole || !Cfg::FINE_EDGES) {
-      // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
-      const bool active = whole || (mi_act > 0 && ni_act > 0);
-      for (int kt = seg.kb; kt < seg.ke; kt++) {
-        mbar_wait(bar_base + 8 * stage, phase);
-        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
-        if (active) {
-          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-          double fa[2][MI], fb[2][NI];
-#pragma unroll
-          for (int i = 0; i < MI; i++) fa[0][i] = lds64(sbase + fa64.addr(i, 0));
-#pragma unroll
-          for (int j = 0; j < NI; j++) fb[0][j] = lds64(sbase + fb64.addr(j, 0));
-#pragma unroll
-          for (int ks = 0; ks < KS; ks++) {
-            const int cur = ks & 1, nxt = cur ^ 1;
-            if (ks + 1 < KS) {
-#pragma unroll
-              for (int i = 0; i < MI; i++) fa[nxt][i] = lds64(sbase + fa64.addr(i, ks + 1));
-#pragma unroll
-              for (int j = 0; j < NI; j++) fb[nxt][j] = lds64(sbase + fb64.addr(j, ks + 1));
-            }
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-#pragma unroll
-              for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[cur][i], fb[cur][j]);
-          }
-        }
-        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    } else {
-      // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
-      for (int kt = seg.kb; kt < seg.ke; kt++) {
-        mbar_wait(bar_base + 8 * stage, phase);
-        if (RTAT_WS_FENCE_WAIT) __threadfence_block();
-        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-        if (mi_act > 0 && ni_act > 0) {
-#pragma unroll
-          for (int ks = 0; ks < KS; ks++) {
-            double fa[MI], fb[NI];
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-              if (i < mi_act) fa[i] = lds64(sbase + fa64.addr(i, ks));
-#pragma unroll
-            for (int j = 0; j < NI; j++)
-              if (j < ni_act) fb[j] = lds64(sbase + fb64.addr(j, ks));
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-              if (i < mi_act) {
-#pragma unroll
-                for (int j = 0; j < NI; j++)
-                  if (j < ni_act) dmma(acc[i][j], fa[i], fb[j]);
-              }
-          }
-        }
-        if (RTAT_WS_FENCE_ARRIVE) __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-
-    }
 
     if (seg.kb > 0) {
       // stream-K contributor: this run started inside the tile.  Park the accumulators
@@ -757,7 +622,6 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   }
-  if (RTAT_WS_PARK && Cfg::SPLIT_REGS && USE_TMA) asm volatile("bar.arrive 2, %0;\n" ::"n"(PARK_THREADS) : "memory");
 }
 
 // ---- host side ---------------------------------------------------------------------------------------

@@ -69,31 +69,44 @@ struct Vec32;
 template <>
 struct Vec32<double> {
   static constexpr int N = 4;
+  // HINT: 0 = default caching, 1 = no L1 allocation + L2 evict-first (data used once), 2 = .cs (streaming) on both sides
+  template <int HINT>
   static __device__ __forceinline__ void load(double (&v)[4], const double *p) {
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    if (HINT == 1) asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    else if (HINT == 2) asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    else asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
   }
+  template <int HINT>
   static __device__ __forceinline__ void store(double *p, const double (&v)[4]) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    if (HINT == 1) asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    else if (HINT == 2) asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    else asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
   }
 };
 template <>
 struct Vec32<float> {
   static constexpr int N = 8;
+#define RTAT_LD8(Q) asm volatile("ld.global" Q ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p))
+#define RTAT_ST8(Q) asm volatile("st.global" Q ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory")
+  template <int HINT>
   static __device__ __forceinline__ void load(float (&v)[8], const float *p) {
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
+    if (HINT == 1) RTAT_LD8(".L1::no_allocate.L2::evict_first");
+    else if (HINT == 2) RTAT_LD8(".cs");
+    else RTAT_LD8("");
   }
+  template <int HINT>
   static __device__ __forceinline__ void store(float *p, const float (&v)[8]) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
-                 "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
+    if (HINT == 1) RTAT_ST8(".L1::no_allocate.L2::evict_first");
+    else if (HINT == 2) RTAT_ST8(".cs");
+    else RTAT_ST8("");
   }
+#undef RTAT_LD8
+#undef RTAT_ST8
 };
 
 // streaming kernel on 32 B vectors (every operand 32 B aligned, ld and m multiples of 32 B): same chunk
 // walk as geam_stream_kernel below
-template <typename T, int MODE, int UNR>
+template <typename T, int MODE, int UNR, int HINT>
 __global__ void __launch_bounds__(256)
 geam_stream256_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb, T *C, int ldc,
                       int chunks_per_col) {
@@ -110,8 +123,8 @@ geam_stream256_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T
     for (int u = 0; u < UNR; u++) {
       const int i = i0 + u * 256 * VN;
       if (i < m) {
-        if (MODE != 1) Vec32<T>::load(va[u], a + i);
-        if (MODE != 0) Vec32<T>::load(vb[u], b + i);
+        if (MODE != 1) Vec32<T>::template load<HINT>(va[u], a + i);
+        if (MODE != 0) Vec32<T>::template load<HINT>(vb[u], b + i);
       }
     }
 #pragma unroll
@@ -121,7 +134,7 @@ geam_stream256_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T
         T out[VN];
 #pragma unroll
         for (int e = 0; e < VN; e++) out[e] = axpby<T, MODE>(alpha, MODE != 1 ? va[u][e] : T(0), beta, MODE != 0 ? vb[u][e] : T(0));
-        Vec32<T>::store(c + i, out);
+        Vec32<T>::template store<HINT>(c + i, out);
       }
     }
   }
@@ -264,19 +277,24 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
                    opt(h, "geam.variant") == 0;
       if (vec32) {
         const int tune = opt(h, "geam.tune");
-        auto go = [&](auto unr_tag, int ctas_per_sm) {
+        auto go = [&](auto unr_tag, int ctas_per_sm, auto hint_tag = std::integral_constant<int, 0>{}) {
           constexpr int UNR = decltype(unr_tag)::value;
+          constexpr int HINT = decltype(hint_tag)::value;
           const int chunk32 = 256 * VN32 * UNR;
           const int cpc = (m + chunk32 - 1) / chunk32;
           const long long tot = (long long)cpc * n;
           const long long cap = (long long)h->sm_count * ctas_per_sm;
           const int g = (int)(tot < cap ? tot : cap);
-          geam_stream256_kernel<T, MODE, UNR><<<g, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, cpc);
+          geam_stream256_kernel<T, MODE, UNR, HINT><<<g, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, cpc);
           return check_launch(h, "geam_stream_vec32");
         };
         // measured on 8192^2 f64 (GB/s): UNR 4 x 8 CTAs/SM 6333 | 1 x 16: 6252 | 2 x 8: 6082 | 2 x 4: 6051 | 1 x 8: 5975
         if (tune == 1) return go(std::integral_constant<int, 2>{}, 8);
         if (tune == 2) return go(std::integral_constant<int, 1>{}, 16);
+        if (tune == 3) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 1>{});
+        if (tune == 4) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 2>{});
+        if (tune == 5) return go(std::integral_constant<int, 2>{}, 16, std::integral_constant<int, 1>{});
+        if (tune == 6) return go(std::integral_constant<int, 8>{}, 4, std::integral_constant<int, 1>{});
         return go(std::integral_constant<int, 4>{}, 8);
       }
     }

@@ -285,6 +285,7 @@ static bool tma_addressable(const T *ptr, int ld) {
   return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ((size_t)ld * sizeof(T)) % 16 == 0;
 }
 
+
 // A may be anything (cp.async producers take over when TMA cannot address it); C and B must be TMA-addressable.
 template <typename T>
 bool geam_transpose_tma_supported(int m, int n, const T *A, int lda, const T *B, int ldb, const T *C, int ldc, bool use_b) {

@@ -571,10 +571,22 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const long long tile_end = (long long)(seg.tile - p.dp_tiles + 1) * p.kt;
       for (int c = blockIdx.x + 1; c < (int)gridDim.x && p.sk_units * c / (long long)gridDim.x < tile_end; c++) {
         if (ctid == 0) {
+          // The contributor is a CTA of this same launch; the grid never exceeds what the occupancy calculator says is
+          // co-resident on an otherwise idle device, so it is running or done.  Should other work hold SMs (a second
+          // stream-K launch on another stream), a contributor may not be scheduled while finishers spin: the wait is
+          // bounded and the kernel then traps, so the failure surfaces as a CUDA error instead of a hung GPU.
           unsigned v;
-          do {
+          unsigned long long t0 = 0;
+          for (unsigned polls = 0;; polls++) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.sk_flags + c) : "memory");
-          } while (v != p.sk_generation);
+            if (v == p.sk_generation) break;
+            if ((polls & 1023u) == 1023u) {
+              unsigned long long now;
+              asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 20000000000ull) __trap();  // 20 s
+            }
+          }
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_WARPS * 32) : "memory");
         const double *slot = p.sk_slots + (size_t)c * SLOT_DOUBLES + ctid;

@@ -277,7 +277,7 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
                    opt(h, "geam.variant") == 0;
       if (vec32) {
         const int tune = opt(h, "geam.tune");
-        auto go = [&](auto unr_tag, int ctas_per_sm, auto hint_tag = std::integral_constant<int, 0>{}) {
+        auto go = [&](auto unr_tag, int ctas_per_sm, auto hint_tag) {
           constexpr int UNR = decltype(unr_tag)::value;
           constexpr int HINT = decltype(hint_tag)::value;
           const int chunk32 = 256 * VN32 * UNR;
@@ -289,13 +289,13 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
           return check_launch(h, "geam_stream_vec32");
         };
         // measured on 8192^2 f64 (GB/s): UNR 4 x 8 CTAs/SM 6333 | 1 x 16: 6252 | 2 x 8: 6082 | 2 x 4: 6051 | 1 x 8: 5975
-        if (tune == 1) return go(std::integral_constant<int, 2>{}, 8);
-        if (tune == 2) return go(std::integral_constant<int, 1>{}, 16);
+        if (tune == 1) return go(std::integral_constant<int, 2>{}, 8, std::integral_constant<int, 0>{});
+        if (tune == 2) return go(std::integral_constant<int, 1>{}, 16, std::integral_constant<int, 0>{});
         if (tune == 3) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 1>{});
         if (tune == 4) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 2>{});
         if (tune == 5) return go(std::integral_constant<int, 2>{}, 16, std::integral_constant<int, 1>{});
         if (tune == 6) return go(std::integral_constant<int, 8>{}, 4, std::integral_constant<int, 1>{});
-        return go(std::integral_constant<int, 4>{}, 8);
+        return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 0>{});
       }
     }
     const int chunk = 256 * (vec ? VN * UNR_V : UNR_S);

@@ -428,6 +428,21 @@ def main():
         chosen = tune[-1]
         in_bytes = (ar * ac + br * bc) * esz
         flush = in_bytes < 200e6
+        # the reference harness's own protocol (src/app/test_harness.h: back-to-back executions, each bracketed by the
+        # executor's Device_Timer events, mean of the last 5 of 8): the planner logs exactly those event pairs
+        def chosen_times():
+            for o in planner.statistics()[0]["options"]:
+                pname = "".join(o["option"][x] for x in ("transA", "transB", "transC", "padA", "padB", "padC") if x in o["option"])
+                if pname == chosen:
+                    return list(o["times"])
+            return []
+        n_before = len(chosen_times())
+        n_event = 8 if 2.0 * m * n * k < 5e12 else 3   # config 5: 1.9 s per execution
+        for _ in range(n_event):
+            step()
+        torch.cuda.synchronize()
+        ev_times = chosen_times()[n_before:]
+        event_ms = statistics.mean(ev_times[-(n_event - (3 if n_event == 8 else 1)):]) if len(ev_times) == n_event else None
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
@@ -473,6 +488,10 @@ def main():
                "l2_policy": "512 MB written between timed steps (inputs fit in the 126 MB L2)" if flush else "inputs larger than L2 (126 MB): no flush needed",
                "roofline": gemm_roofline(dtype, name, flops / (k_ms * 1e-3) * 1e-12, gemm_kernel, m, n, k, k_ms),
                "parity_check": parity}
+        if event_ms is not None:
+            out["event_time"] = {"ms": event_ms, "value": flops / (event_ms * 1e-3) * 1e-12,
+                                 "note": "mean of the executor's own Device_Timer samples over the last 5 of 8 (config 5: 2 of 3) back-to-back executions of the chosen plan: "
+                                         "the measurement the reference's run_tests reports"}
         if warm_ms:
             out["warm_l2"] = {"ms_per_step": statistics.mean(warm_ms), "value": flops / (statistics.mean(warm_ms) * 1e-3) * 1e-12,
                               "note": "back-to-back steps, inputs L2-resident: the case the reference's harness measures"}
@@ -701,12 +720,15 @@ def main():
         # the unmodified reference on the same problems (its own driver / MatrixMove over cuBLAS), same GPU, same run
         for name in ("c1", "c2", "c3", "c4"):
             ref = reference_run_tests(CONFIGS[name], 8, 3)
-            ours_ms = per[name].get("warm_l2", per[name])["ms_per_step"]
+            step_ms = per[name].get("warm_l2", per[name])["ms_per_step"]
+            ours_ms = per[name].get("event_time", {}).get("ms", step_ms)
             if ref and "best_ms" in ref:
                 per[name]["vs_reference"] = {"reference_ms": ref["best_ms"], "reference_plan": ref["best_plan"], "reference_tflops": ref["tflops"],
                                              "ours_ms": ours_ms, "ratio": ref["best_ms"] / ours_ms,
-                                             "note": "oracle/_ref/run_tests (unmodified reference, cuBLAS 12.9), exhaustive over its plans, mean of 5 samples after 3; "
-                                                     "ours = planner steps back to back (warm L2 where the inputs fit, as the reference's harness measures)"}
+                                             "ours_step_ms": step_ms, "ratio_step": ref["best_ms"] / step_ms,
+                                             "note": "oracle/_ref/run_tests (unmodified reference, cuBLAS 12.9), exhaustive over its plans, mean of 5 Device_Timer samples after 3; "
+                                                     "ratio: ours measured the same way (event_time: the executor's Device_Timer pairs, back to back, warm L2); "
+                                                     "ratio_step: our whole planner step (events, launch gaps and host path included) against the reference's kernel-only event time"}
             else:
                 per[name]["vs_reference"] = ref
         mv = reference_moves(20)

@@ -76,6 +76,31 @@ if which in ("all", "dgemm"):
     dgemm_cfg("dgemm NN 4096^3", 0, 0, 4096, 4096, 4096)
     dgemm_cfg("dgemm NN 2048^3", 0, 0, 2048, 2048, 2048)
     dgemm_cfg("C5/8-like NN 8192x1024x8192", 0, 0, 8192, 1024, 8192)
+if which == "c3":
+    for split in (1, 0):
+        h.set_option("dgemm.splitk_tma", split)
+        for t in (0, 64, 128):
+            h.set_option("dgemm.tile", t)
+            print("splitk_tma", split, "tile", t, end="  ")
+            dgemm_cfg("C3 dgemm NT 4097x3001x2049", 0, 1, 4097, 3001, 2049, variants=(3,))
+    h.set_option("dgemm.tile", 0); h.set_option("dgemm.splitk_tma", 1)
+    dgemm_cfg("dgemm NN 4097x4096x4096 (A odd ld)", 0, 0, 4097, 4096, 4096, variants=(3, 4))
+    dgemm_cfg("dgemm NT 8191^3", 0, 1, 8191, 8191, 8191, variants=(3, 4))
+if which == "beta":
+    # K-panel products of the host pipeline: 8192 x 4096 x 1024 with beta = 1 (config 2's phase 1) and the TRSM update shape
+    for name, ta, tb, m, n, k in [("panel TN 8192x4096x1024", 1, 0, 8192, 4096, 1024), ("panel NN 8192x4096x1024", 0, 0, 8192, 4096, 1024),
+                                  ("update NN 1024x8192x1024", 0, 0, 1024, 8192, 1024), ("mg panel NN 32768x4096x2048", 0, 0, 32768, 4096, 2048)]:
+        ar, ac = (k, m) if ta else (m, k)
+        br, bc = (n, k) if tb else (k, n)
+        A = torch.empty(ar * ac, dtype=torch.float64, device="cuda"); h.fill_uniform(A, 1)
+        B = torch.empty(br * bc, dtype=torch.float64, device="cuda"); h.fill_uniform(B, 2)
+        Cm = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+        for beta in (0.0, 1.0):
+            for pf in (1, 0):
+                h.set_option("dgemm.prefetch_c", pf)
+                ms = timeit(lambda: h.gemm(True, ta, tb, m, n, k, 1.0, A, ar, B, br, beta, Cm, m))
+                print(f"{name:30s} beta={beta} prefetch_c={pf} {h.last_kernel():36s} {ms:9.3f} ms {2.0*m*n*k/ms*1e-9:8.2f} TFLOP/s", flush=True)
+    h.set_option("dgemm.prefetch_c", 1)
 if which == "geam_tune":
     for t in range(7):
         h.set_option("geam.tune", t)

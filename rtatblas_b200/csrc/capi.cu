@@ -94,6 +94,7 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   if (h->arena) cudaFree(h->arena);
   if (h->staging) cudaFree(h->staging);
   if (h->trsm_inv) cudaFree(h->trsm_inv);
+  if (h->sgemm_a_pad) cudaFree(h->sgemm_a_pad);
   if (h->sk_flags) cudaFree(h->sk_flags);
   if (h->order_event) cudaEventDestroy(h->order_event);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);

@@ -19,6 +19,9 @@ struct rtat_b200_context {
   // TRSM: inverted 32 x 32 diagonal blocks of the current call (separate from the arena, which the GEMM updates use)
   void *trsm_inv = nullptr;
   size_t trsm_inv_bytes = 0;
+  // SGEMM: 16 B-aligned copy of an op(A) TMA cannot address (leading dimension not a multiple of 4 floats, 4 / 8 B base)
+  void *sgemm_a_pad = nullptr;
+  size_t sgemm_a_pad_bytes = 0;
   // Library-owned scratch (arena, trsm_inv, stream-K flags) is ordered by the stream the work runs on.  When the
   // caller rebinds the handle to another stream while such work may still be queued, set_stream makes the new stream
   // wait for it, so a later call cannot overwrite scratch an earlier one is still reading.

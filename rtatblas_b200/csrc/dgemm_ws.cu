@@ -89,6 +89,7 @@ struct Params {
   // panel drift apart in k, and an evict_first line is gone before the laggard asks for it.
   unsigned long long l2_a, l2_b;
   int a_3d, b_3d;  // the operand's map is the 3-D view (see tma_load_3d)
+  int prefetch_c;  // beta != 0: consumers prefetch their part of the C tile into L2 when the tile starts (option dgemm.prefetch_c)
 };
 
 // Tile t of a triangular enumeration -> (i, j) with i >= j: t = i (i + 1) / 2 + j.
@@ -481,6 +482,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   SegmentIter it(p, blockIdx.x, gridDim.x);
   Segment seg;
+  const bool opt_prefetch_c = p.prefetch_c != 0;
   const int ctid = threadIdx.x;  // 0..255 (consumer threads come first)
   constexpr int SLOT_DOUBLES = Cfg::SLOT_DOUBLES;
   while (it.next(seg)) {
@@ -491,6 +493,19 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     for (int i = 0; i < MI; i++)
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // beta != 0: the epilogue reads C.  Its loads come in batches of MI per column, each batch paying one memory latency
+    // (C aliases itself, so loads cannot be hoisted over the stores); from DRAM that is ~1 us x 2 NI batches per tile, 5-7 %
+    // of a 1024-deep product.  Ask for the warp's part of the C tile now, so that the epilogue finds it in L2.
+    if (beta != 0.0 && seg.kb == 0 && opt_prefetch_c) {
+      const int col = n0 + wn0 + lane;
+      if (lane < WN && col < p.n) {
+        const double *c0 = p.C + (size_t)col * p.ldc + m0 + wm0;
+#pragma unroll
+        for (int r = 0; r < WM; r += 16)
+          if (m0 + wm0 + r < p.m) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(c0 + r));
+      }
+    }
 
     // DMMA blocks of this warp that touch C: a ragged tile's consumers skip the rest (blocks are 8 rows / columns of a
     // K-contiguous operand, pairs of blocks interleave within 16 of an M/N-contiguous one)
@@ -600,35 +615,48 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
 
-    // epilogue: lane (q,g) of block (i,j) holds C[row(i,g)][col(j,2q+e)].  With beta != 0 the MI loads of a column
-    // are issued together before the first store: a load-modify-store loop would serialise on one DRAM latency per
-    // element (C aliases itself, so the compiler cannot hoist the loads).
+    // epilogue: lane (q,g) of block (i,j) holds C[row(i,g)][col(j,2q+e)].  With beta != 0 the loads of EPI_COLS columns
+    // (MI each) are issued together before the first store: a load-modify-store loop would serialise on one memory
+    // latency per element (C aliases itself, so the compiler cannot hoist the loads), and nothing else runs on this SM
+    // while its consumers are in the epilogue.  The fragment registers are dead here, which is what pays for the batch.
+#ifndef RTAT_DGEMM_EPI_COLS
+#define RTAT_DGEMM_EPI_COLS 2
+#endif
+    constexpr int EPI_COLS = RTAT_DGEMM_EPI_COLS;
+    static_assert((2 * NI) % EPI_COLS == 0, "columns per thread divide into batches");
 #pragma unroll
-    for (int j = 0; j < NI; j++) {
+    for (int c0 = 0; c0 < 2 * NI; c0 += EPI_COLS) {
+      bool ok[EPI_COLS][MI];
+      double old[EPI_COLS][MI];
+      double *ccol[EPI_COLS];
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        int col = n0 + wn0 + col_of(j, 2 * q + e);
-        if (col >= p.n) continue;
-        double *ccol = p.C + (size_t)col * p.ldc;
-        bool ok[MI];
-        double old[MI];
+      for (int c = 0; c < EPI_COLS; c++) {
+        const int j = (c0 + c) >> 1, e = (c0 + c) & 1;
+        const int col = n0 + wn0 + col_of(j, 2 * q + e);
+        ccol[c] = p.C + (size_t)col * p.ldc;
 #pragma unroll
         for (int i = 0; i < MI; i++) {
-          int row = m0 + wm0 + row_of(i, g);
-          ok[i] = row < p.m && !(TRI && (p.tri == 1 ? row < col : row > col));
-          old[i] = 0.0;
+          const int row = m0 + wm0 + row_of(i, g);
+          ok[c][i] = col < p.n && row < p.m && !(TRI && (p.tri == 1 ? row < col : row > col));
+          old[c][i] = 0.0;
         }
-        if (beta != 0.0) {
+      }
+      if (beta != 0.0) {
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; c++)
 #pragma unroll
           for (int i = 0; i < MI; i++)
-            if (ok[i]) old[i] = ccol[m0 + wm0 + row_of(i, g)];
-        }
+            if (ok[c][i]) old[c][i] = ccol[c][m0 + wm0 + row_of(i, g)];
+      }
+#pragma unroll
+      for (int c = 0; c < EPI_COLS; c++) {
+        const int j = (c0 + c) >> 1, e = (c0 + c) & 1;
 #pragma unroll
         for (int i = 0; i < MI; i++) {
-          if (ok[i]) {
+          if (ok[c][i]) {
             double v = alpha * acc[i][j][e];
-            if (beta != 0.0) v += beta * old[i];
-            ccol[m0 + wm0 + row_of(i, g)] = v;
+            if (beta != 0.0) v += beta * old[c][i];
+            ccol[c][m0 + wm0 + row_of(i, g)] = v;
           }
         }
       }
@@ -814,6 +842,7 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
     p.sk_flags = static_cast<unsigned *>(h->sk_flags);
     p.sk_generation = ++h->sk_generation;
   }
+  p.prefetch_c = opt(h, "dgemm.prefetch_c", 1);
   const bool hints = !tri && opt(h, "dgemm.l2_hints", 0) != 0;
   p.l2_a = hints ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   p.l2_b = hints ? L2_EVICT_FIRST : L2_EVICT_NORMAL;

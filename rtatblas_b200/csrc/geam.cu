@@ -258,6 +258,131 @@ geam_tile_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// register-blocked transpose (A transposed, B not):  C (m x n) = alpha * A^T + beta * B,  A is n x m.
+// One CTA = one tile of TJ (A's contiguous dimension, j) x TI (C's contiguous dimension, i) elements, launched as a plain
+// grid of small CTAs (several resident per SM, the hardware scheduler balancing them), every global access a full
+// 16-byte vector where the operand allows it:
+//   phase 1  a thread loads E = 16 / sizeof(T) vectors from E consecutive rows i of A (a warp covers 512 contiguous bytes
+//            of each row), transposes the E x E block in registers and stores E 16-byte UNITS — E consecutive i of one
+//            column j — to shared memory.  Units of column j sit at j * UPC + (u ^ swz(j)): the XOR makes the eight lanes of
+//            a quarter warp, which write eight different columns, hit eight different 16-byte bank groups.
+//   phase 2  a warp reads whole columns of units back (a permutation of consecutive addresses: conflict-free), applies
+//            alpha / beta and stores 512 contiguous bytes of a column of C per instruction.
+// VEC_IN / VEC_OUT = false: that side is accessed element by element, still one contiguous run per warp instruction
+// (odd leading dimensions, bases off 16 bytes, extents that are not a multiple of E): then a lane owns columns
+// lane + 32 e instead of E lane + e (phase 1) or reads single elements of the units (phase 2).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Unit16 { T v[16 / sizeof(T)]; };
+
+#ifndef RTAT_GEAM_TR_MINB
+#define RTAT_GEAM_TR_MINB 1  // probe builds raise this (resident CTAs per SM the register allocation must allow)
+#endif
+template <typename T, bool USE_B, bool VEC_IN, bool VEC_OUT, int UPC>
+__global__ void __launch_bounds__(256, RTAT_GEAM_TR_MINB)
+geam_transpose_reg_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb, T *C, int ldc,
+                          int tiles_m, int tiles_n, int order) {
+  constexpr int E = 16 / sizeof(T);
+  constexpr int TJ = 32 * E;                       // 64 doubles / 128 floats: 512 B of every row of A
+  constexpr int TI = UPC * E;                      // UPC units per column: 32 or 64 elements
+  static_assert(UPC % 8 == 0 && TI % 32 == 0 && UPC <= 32, "swizzle period; scalar phase 2 moves 32 elements of a column per instruction");
+  using V = typename Vec16<T>::type;
+  __shared__ __align__(16) T s[TJ * TI];           // 16 or 32 KB
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // order 0: consecutive CTAs walk down C's contiguous dimension (adjacent 512 B pieces of the same columns of C);
+  // order 1: along A's contiguous dimension (adjacent pieces of the same rows of A)
+  const int ti = order ? blockIdx.x / tiles_n : blockIdx.x % tiles_m, tj = order ? blockIdx.x % tiles_n : blockIdx.x / tiles_m;
+  const int i0 = ti * TI, j0 = tj * TJ;
+  auto swz = [](int jl) { return (VEC_IN ? jl / E : jl) & 7; };
+  auto col_of = [&](int e) { return VEC_IN ? E * lane + e : lane + 32 * e; };
+
+  // ---- phase 1
+#pragma unroll
+  for (int g = warp; g < UPC; g += 8) {
+    T a[E][E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const int i = i0 + g * E + r;
+      if (VEC_IN) {
+        const int j = j0 + E * lane;
+        V v = V();
+        if (i < m && j < n) v = __ldcs(reinterpret_cast<const V *>(A + (size_t)i * lda + j));
+        const T *pv = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int e = 0; e < E; e++) a[r][e] = pv[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int j = j0 + lane + 32 * e;
+          a[r][e] = (i < m && j < n) ? __ldcs(A + (size_t)i * lda + j) : T(0);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int jl = col_of(e);
+      Unit16<T> u;
+#pragma unroll
+      for (int r = 0; r < E; r++) u.v[r] = a[r][e];
+      *reinterpret_cast<V *>(&s[(jl * UPC + (g ^ swz(jl))) * E]) = *reinterpret_cast<V *>(&u);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2
+  if (VEC_OUT) {
+    constexpr int CPI = 32 / UPC;            // columns per warp instruction
+    constexpr int ITER = TJ / CPI / 8;       // 8
+    const int u = lane % UPC;
+    const int i = i0 + u * E;
+    V bv[ITER];
+    if (USE_B) {
+#pragma unroll
+      for (int t = 0; t < ITER; t++) {
+        const int j = j0 + (t * 8 + warp) * CPI + lane / UPC;
+        if (j < n && i < m) bv[t] = *reinterpret_cast<const V *>(B + (size_t)j * ldb + i);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < ITER; t++) {
+      const int jl = (t * 8 + warp) * CPI + lane / UPC, j = j0 + jl;
+      if (j < n && i < m) {
+        V av = *reinterpret_cast<const V *>(&s[(jl * UPC + (u ^ swz(jl))) * E]);
+        const T *pa = reinterpret_cast<const T *>(&av);
+        const T *pb = reinterpret_cast<const T *>(&bv[t]);
+        V out;
+        T *po = reinterpret_cast<T *>(&out);
+#pragma unroll
+        for (int e = 0; e < E; e++) po[e] = axpby<T, USE_B ? 4 : 0>(alpha, pa[e], beta, USE_B ? pb[e] : T(0));
+        __stcs(reinterpret_cast<V *>(C + (size_t)j * ldc + i), out);
+      }
+    }
+  } else {
+    constexpr int RPC = TI / 32;             // warp instructions per column (2)
+    constexpr int ITER = TJ * RPC / 8;       // 16 / 32
+    constexpr int BATCH = 8;
+#pragma unroll
+    for (int t0 = 0; t0 < ITER; t0 += BATCH) {
+      T bv[BATCH];
+      if (USE_B) {
+#pragma unroll
+        for (int t = 0; t < BATCH; t++) {
+          const int x = (t0 + t) * 8 + warp, jl = x / RPC, il = (x % RPC) * 32 + lane;
+          if (j0 + jl < n && i0 + il < m) bv[t] = B[(size_t)(j0 + jl) * ldb + i0 + il];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < BATCH; t++) {
+        const int x = (t0 + t) * 8 + warp, jl = x / RPC, il = (x % RPC) * 32 + lane;
+        if (j0 + jl < n && i0 + il < m) {
+          const T av = s[(jl * UPC + ((il / E) ^ swz(jl))) * E + il % E];
+          __stcs(C + (size_t)(j0 + jl) * ldc + i0 + il, axpby<T, USE_B ? 4 : 0>(alpha, av, beta, USE_B ? bv[t] : T(0)));
+        }
+      }
+    }
+  }
+}
+
 template <typename T, int MODE>
 static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int n, T alpha, const T *A,
                        int lda, T beta, const T *B, int ldb, T *C, int ldc) {
@@ -295,13 +420,23 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
         if (tune == 4) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 2>{});
         if (tune == 5) return go(std::integral_constant<int, 2>{}, 16, std::integral_constant<int, 1>{});
         if (tune == 6) return go(std::integral_constant<int, 8>{}, 4, std::integral_constant<int, 1>{});
-        return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 0>{});
+        // one chunk per CTA, as many CTAs as chunks (the hardware scheduler hands them out): 8 / 16 / 32 KB per CTA
+        if (tune == 7) return go(std::integral_constant<int, 1>{}, 1 << 20, std::integral_constant<int, 0>{});
+        if (tune == 8) return go(std::integral_constant<int, 2>{}, 1 << 20, std::integral_constant<int, 0>{});
+        if (tune == 9) return go(std::integral_constant<int, 4>{}, 1 << 20, std::integral_constant<int, 0>{});
+        if (tune == 10) return go(std::integral_constant<int, 1>{}, 1 << 20, std::integral_constant<int, 2>{});
+        if (tune == 11) return go(std::integral_constant<int, 2>{}, 1 << 20, std::integral_constant<int, 2>{});
+        if (tune == 12) return go(std::integral_constant<int, 4>{}, 8, std::integral_constant<int, 0>{});  // the persistent grid of round 1
+        // default: one 8 KB chunk per CTA.  8192^2 f64: 6784 GB/s against 6429 for the persistent grid and 6655-6810 for cublasDgeam
+        return go(std::integral_constant<int, 1>{}, 1 << 20, std::integral_constant<int, 0>{});
       }
     }
     const int chunk = 256 * (vec ? VN * UNR_V : UNR_S);
     const int chunks_per_col = (m + chunk - 1) / chunk;
     const long long total = (long long)chunks_per_col * n;
-    const int grid = (int)(total < max_ctas ? total : max_ctas);
+    // one chunk per CTA (see the 32-byte path above); geam.persistent = 1 restores the grid-stride walk over 8 CTAs per SM
+    const long long cap = opt(h, "geam.persistent") ? (long long)max_ctas : 0x7fffffffLL;
+    const int grid = (int)(total < cap ? total : cap);
     if (vec) {
       geam_stream_kernel<T, MODE, true, UNR_V><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col);
       return check_launch(h, "geam_stream_vec16");
@@ -313,7 +448,35 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
   int tiles_m = (m + TL - 1) / TL, tiles_n = (n + TL - 1) / TL;
   long long tiles = (long long)tiles_m * tiles_n;
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-  if (ta && !tb && (MODE == 0 || MODE == 4) && opt(h, "geam.variant") != 1 &&
+  // geam.transpose: 0 = choose, 1 = TMA pipeline (geam_tma.cu), 2 = register-blocked kernel above, 3 = scalar tile kernel
+  const int tsel = opt(h, "geam.transpose");
+  if (ta && !tb && (MODE == 0 || MODE == 4) && opt(h, "geam.variant") != 1 && (tsel == 0 || tsel == 2)) {
+    constexpr int E = 16 / (int)sizeof(T);
+    constexpr int TJ = 32 * E;
+    // units (16 B) per column of the tile: tiles of 64 x 32 doubles / 128 x 32 floats (16 KB) by default, twice that with
+    // geam.upc = 2 (measured on 8192^2: see DESIGN.md §3)
+    constexpr int UPC_S = 32 / E, UPC_L = 64 / E;
+    const bool large = opt(h, "geam.upc") == 2;
+    const int TI = (large ? UPC_L : UPC_S) * E;
+    auto al16 = [&](const T *p, int ld) { return reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % E == 0; };
+    const bool vin = al16(A, lda) && n % E == 0;
+    const bool vout = al16(C, ldc) && m % E == 0 && (MODE == 0 || al16(B, ldb));
+    const int tm = (m + TI - 1) / TI, tn = (n + TJ - 1) / TJ;
+    if ((long long)tm * tn <= 0x7fffffffLL) {
+      const int order = opt(h, "geam.order");
+      constexpr bool UB = MODE != 0;
+#define RTAT_TR(VI, VO)                                                                                                                 \
+  if (large) geam_transpose_reg_kernel<T, UB, VI, VO, UPC_L><<<tm * tn, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tm, tn, order); \
+  else geam_transpose_reg_kernel<T, UB, VI, VO, UPC_S><<<tm * tn, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, tm, tn, order)
+      if (vin && vout) { RTAT_TR(true, true); return check_launch(h, "geam_transpose_reg_v16_v16"); }
+      if (vin) { RTAT_TR(true, false); return check_launch(h, "geam_transpose_reg_v16_s"); }
+      if (vout) { RTAT_TR(false, true); return check_launch(h, "geam_transpose_reg_s_v16"); }
+      RTAT_TR(false, false);
+      return check_launch(h, "geam_transpose_reg_s_s");
+#undef RTAT_TR
+    }
+  }
+  if (ta && !tb && (MODE == 0 || MODE == 4) && opt(h, "geam.variant") != 1 && tsel != 3 &&
       geam_transpose_tma_supported<T>(m, n, A, lda, B, ldb, C, ldc, MODE != 0)) {
     int st = geam_transpose_tma<T>(h, m, n, alpha, A, lda, MODE == 0 ? T(0) : beta, B, ldb, C, ldc);
     if (st != RTAT_B200_STATUS_NOT_SUPPORTED) return st;

@@ -9,7 +9,7 @@
 //
 // The tensor core adds into its FP32 accumulator with truncation, so a long accumulation chain at
 // full magnitude drifts by ~(k/8) half-ulps (measured: 3e-3 absolute at k = 4096, 12x an FP32 FMA
-// chain).  The accumulator is therefore promoted every CHUNK_KB k-blocks (128 k): the epilogue warps
+// chain).  The accumulator is therefore promoted every CHUNK_KB k-blocks (256 k): the epilogue warps
 // drain it from TMEM and add it, with round-to-nearest, into FP32 registers while the MMAs continue
 // in the twin accumulator; inside a chunk the partial sums are small, and so are their ulps.
 //
@@ -59,7 +59,14 @@ constexpr int TMEM_A0 = 256;                       // first TMEM column of the A
 constexpr int NUM_THREADS = 320;
 constexpr int SPLIT_WARP0 = 0, EPI_WARP0 = 4, TMA_WARP = 8, MMA_WARP = 9;
 constexpr int TMEM_COLS = 512;   // two accumulators + four A staging slots
-constexpr int CHUNK_KB = 4;      // promote the big accumulator every 4 k-blocks = 128 k
+// Promote the accumulator every CHUNK_KB k-blocks (8 = 256 k).  The drain is not free: tcgen05.ld of 64 KB of
+// accumulators per chunk competes with the MMAs for tensor memory (config 4, CTA pairs: 0.599 ms at 4, 0.553 at 8, 0.570
+// at 16; 8192^3: 203 / 217 / 229 TFLOP/s), while the truncation drift inside a chunk grows only with the square root
+// of its length; 8 keeps the error within 4x an FP32 FMA chain's (tests/test_gpu_parity.py, accuracy class test).
+#ifndef RTAT_SGEMM_CHUNK_KB
+#define RTAT_SGEMM_CHUNK_KB 8
+#endif
+constexpr int CHUNK_KB = RTAT_SGEMM_CHUNK_KB;
 constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 + 256;
 
 struct Params {
@@ -456,10 +463,15 @@ constexpr int BN_HALF = BN / 2;
 constexpr int B_HALF_BYTES = BN_HALF * BK * 4;             // 8 KB
 constexpr int STAGE_BYTES = TILE_BYTES + 2 * B_HALF_BYTES;  // A raw + B big half + B small half = 32 KB
 #ifndef RTAT_SGEMM_PAIR_STAGES
-#define RTAT_SGEMM_PAIR_STAGES 4
+#define RTAT_SGEMM_PAIR_STAGES 6
 #endif
-constexpr int STAGES = RTAT_SGEMM_PAIR_STAGES;  // tensor memory holds four A staging slots next to the two accumulators
-static_assert(STAGES <= 4, "one tensor-memory A slot (64 columns) per stage: 256 + 64 * STAGES <= 512");
+// The shared-memory ring (what TMA fills) is deeper than the tensor-memory ring of split A tiles: the first has to cover
+// the L2 latency of a machine whose L2 -> SM path runs at its limit (config 4 moves 42 B/clk into every SM; four 32 KB
+// stages covered barely 3000 cycles, and the pair ran latency-bound at 56 % tensor-pipe activity), the second only the
+// split -> MMA hand-off.  k-block i of a CTA uses shared-memory stage i % STAGES and tensor-memory slot i % TSLOTS.
+constexpr int STAGES = RTAT_SGEMM_PAIR_STAGES;
+constexpr int TSLOTS = 4;  // 64 tensor-memory columns each (32 big + 32 small), next to the two 128-column accumulators
+static_assert(STAGES >= TSLOTS && STAGES <= 7, "7 x 32 KB is what fits in 227 KB of shared memory");
 constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -580,7 +592,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     // ===================== MMA issuer: the leader CTA's elected lane drives both tensor cores =====================
     if (rank == 0) {
       constexpr uint32_t idesc = make_instr_desc(false, !KCB, 2 * BM, BN);  // M = 256 across the pair; A from TMEM: K-major
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, tslot = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
         for (int kb = 0; kb < p.kb; kb++) {
@@ -590,7 +602,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (elect_one()) {
             const uint32_t d = tmem_base + acc * BN;
-            const uint32_t a_big_t = tmem_base + TMEM_A0 + 64 * stage, a_small_t = a_big_t + 32;
+            const uint32_t a_big_t = tmem_base + TMEM_A0 + 64 * tslot, a_small_t = a_big_t + 32;
             const uint32_t sB = smem_base + stage * STAGE_BYTES + TILE_BYTES, sBs = sB + B_HALF_BYTES;
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ks++) {
@@ -604,6 +616,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++tslot == TSLOTS) tslot = 0;
           if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -614,10 +627,15 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     const int quarter = warp - SPLIT_WARP0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t conv_leader = map_to_cta(conv0, 0);
-    int stage = 0;
+    int stage = 0, tslot = 0;
     uint32_t phase = 0;
+    // tensor-memory slot i % TSLOTS may be rewritten once the MMAs of k-block i - TSLOTS are complete, which is what the
+    // commit on that k-block's `empty` barrier reports: (old_stage, old_phase) trail (stage, phase) by TSLOTS k-blocks.
+    // The barrier cannot run a whole phase ahead of this wait: its next completion needs k-block i - TSLOTS + STAGES > i.
+    int it = 0, old_stage = 0;
+    uint32_t old_phase = 0;
     for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
-      for (int kb = 0; kb < p.kb; kb++) {
+      for (int kb = 0; kb < p.kb; kb++, it++) {
         mbar_wait(full0 + 8 * stage, phase);
         const uint32_t sA = smem_base + stage * STAGE_BYTES;
         uint32_t big[32], small[32];
@@ -642,7 +660,12 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             small[kk] = to_tf32(x - __uint_as_float(big[kk]));
           }
         }
-        const uint32_t ta = lane_base + TMEM_A0 + 64 * stage;
+        if (STAGES > TSLOTS && it >= TSLOTS) {
+          mbar_wait(empty0 + 8 * old_stage, old_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (++old_stage == STAGES) { old_stage = 0; old_phase ^= 1; }
+        }
+        const uint32_t ta = lane_base + TMEM_A0 + 64 * tslot;
         tmem_st32(ta, big);
         tmem_st32(ta + 32, small);
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -650,6 +673,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++tslot == TSLOTS) tslot = 0;
       }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
@@ -762,10 +786,22 @@ static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k) {
   return m > tc::BM && bytes_n <= PRESPLIT_LIMIT && bytes_t <= PRESPLIT_LIMIT;
 }
 
-bool sgemm_tcgen05_supported(const rtat_b200_context *h, int, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
+// An op(A) TMA cannot address is first copied into a 16 B-aligned buffer owned by the handle (one streaming pass over A,
+// geam.cu: ~7 TB/s) — for anything but a very thin product that is a few per cent of the multiply, where the FP32 SIMT
+// fallback runs at a fifth of this kernel's rate (4097^3: 3.4 ms against ~0.65).  Not for more than PAD_A_LIMIT bytes of A
+// (the copy doubles A's footprint) and not when the product does too little work per element of A to pay for the pass.
+constexpr size_t PAD_A_LIMIT = size_t(1) << 30;
+static bool pad_a_wanted(const rtat_b200_context *h, bool ta, int m, int n, int k) {
+  if (opt(h, "sgemm.pad_a", 1) == 0) return false;
+  const size_t rows = ta ? k : m, cols = ta ? m : k;
+  return n >= 64 && sizeof(float) * ((rows + 3) / 4 * 4) * cols <= PAD_A_LIMIT;
+}
+
+bool sgemm_tcgen05_supported(const rtat_b200_context *h, int transa, int, int m, int n, int k, const float *A, int lda, const float *B, int ldb,
                              const float *, int) {
   auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 4 == 0; };
-  if (!(m > 0 && n > 0 && k > 0) || !ok(A, lda)) return false;
+  if (!(m > 0 && n > 0 && k > 0)) return false;
+  if (!ok(A, lda) && !pad_a_wanted(h, transa == RTAT_B200_OP_T, m, n, k)) return false;
   return ok(B, ldb) || presplit_wanted(h, m, n, k);
 }
 
@@ -784,6 +820,32 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   p.num_tiles = (int)tiles;
   p.kb = (k + BK - 1) / BK;
+  bool padded_a = false;
+  if (reinterpret_cast<uintptr_t>(A) % 16 != 0 || lda % 4 != 0) {
+    if (!pad_a_wanted(h, ta, m, n, k)) return RTAT_B200_STATUS_NOT_SUPPORTED;
+    const int rows = ta ? k : m, cols = ta ? m : k, ldp = (rows + 3) / 4 * 4;
+    const size_t need = sizeof(float) * (size_t)ldp * cols;
+    if (need > h->sgemm_a_pad_bytes) {
+      if (h->sgemm_a_pad) {
+        cudaStreamSynchronize(h->stream);  // an earlier product may still be reading the old copy
+        cudaFree(h->sgemm_a_pad);
+        h->sgemm_a_pad = nullptr;
+        h->sgemm_a_pad_bytes = 0;
+      }
+      const size_t want = (need + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+      if (cudaMalloc(&h->sgemm_a_pad, want) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return RTAT_B200_STATUS_ALLOC_FAILED;
+      }
+      h->sgemm_a_pad_bytes = want;
+    }
+    h->scratch_in_flight = true;
+    float *Ap = static_cast<float *>(h->sgemm_a_pad);
+    if (int st = geam<float>(h, RTAT_B200_OP_N, RTAT_B200_OP_N, rows, cols, 1.f, A, lda, 0.f, Ap, ldp, Ap, ldp)) return st;
+    A = Ap;
+    lda = ldp;
+    padded_a = true;
+  }
   const bool presplit = presplit_wanted(h, m, n, k);
   const float *Bbig = B, *Bsmall = B;
   int ldb_eff = ldb;
@@ -814,17 +876,18 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   ok = ok && (!tb ? make_map(&mb, Bbig, k, n, ldb_eff, BK, bn_box, kmaj) : make_map(&mb, Bbig, n, k, ldb_eff, 32, BK, mnmaj));
   ok = ok && (!tb ? make_map(&mbs, Bsmall, k, n, ldb_eff, BK, bn_box, kmaj) : make_map(&mbs, Bsmall, n, k, ldb_eff, 32, BK, mnmaj));
   if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  if (use_pair) {
-    if (!ta && !tb) return launch_pair<false, false>(h, p, ma, mb, mbs);
-    if (ta && !tb) return launch_pair<true, false>(h, p, ma, mb, mbs);
-    if (!ta && tb) return launch_pair<false, true>(h, p, ma, mb, mbs);
-    return launch_pair<true, true>(h, p, ma, mb, mbs);
+  int st;
+#define RTAT_TC(TA_, TB_) (use_pair ? launch_pair<TA_, TB_>(h, p, ma, mb, mbs) : presplit ? launch<TA_, TB_, true>(h, p, ma, mb, mbs) : launch<TA_, TB_, false>(h, p, ma, mb, mbs))
+  if (!ta && !tb) st = RTAT_TC(false, false);
+  else if (ta && !tb) st = RTAT_TC(true, false);
+  else if (!ta && tb) st = RTAT_TC(false, true);
+  else st = RTAT_TC(true, true);
+  if (st == RTAT_B200_STATUS_SUCCESS && padded_a) {  // reported name: <kernel>_padA
+    static thread_local char name[96];
+    snprintf(name, sizeof name, "%s_padA", h->last_kernel);
+    h->last_kernel = name;
   }
-#define RTAT_TC(TA_, TB_) (presplit ? launch<TA_, TB_, true>(h, p, ma, mb, mbs) : launch<TA_, TB_, false>(h, p, ma, mb, mbs))
-  if (!ta && !tb) return RTAT_TC(false, false);
-  if (ta && !tb) return RTAT_TC(true, false);
-  if (!ta && tb) return RTAT_TC(false, true);
-  return RTAT_TC(true, true);
+  return st;
 #undef RTAT_TC
 }
 

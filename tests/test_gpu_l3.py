@@ -87,6 +87,12 @@ def test_ssyrk_runs_on_tcgen05(oracle, handle):
             name = _syrk_case(oracle, handle, np.float32, lower, trans, 384, 512, 1.0, 0.0, 650)
             assert name.startswith("ssyrk_tcgen05_3xtf32"), name
             name = _syrk_case(oracle, handle, np.float32, lower, trans, 200, 96, 1.0, 0.5, 660, lda_pad=1)
+            assert name.startswith("ssyrk_tcgen05_3xtf32") and name.endswith("_padA"), name  # odd ld: aligned copy of A first
+            handle.set_option("sgemm.pad_a", 0)
+            try:
+                name = _syrk_case(oracle, handle, np.float32, lower, trans, 200, 96, 1.0, 0.5, 660, lda_pad=1)
+            finally:
+                handle.set_option("sgemm.pad_a", 1)
             assert name.startswith("ssyrk_simt"), name
 
 

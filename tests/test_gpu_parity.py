@@ -193,19 +193,26 @@ def test_geam_accumulate_and_general(oracle, handle, dtype):
 
 
 def test_geam_transpose_paths_agree_bitwise(oracle, handle):
-    """TMA transpose kernel vs the LSU tile kernel on a shape with ragged 64x64 edge tiles."""
+    """The three transposing kernels — register-blocked (the default), TMA pipeline, scalar tile — on a shape with ragged edge
+    tiles, either CTA order and tile height of the default kernel: bit-identical, and equal to the transpose."""
     for dtype in (np.float64, np.float32):
         m, n = 1000, 1100
         A = dev(oracle.fill(n * m, 5, dtype))
         outs = []
-        for variant in (0, 1):
-            handle.set_option("geam.variant", variant)
-            Cm = torch.full((m * n,), float("nan"), dtype=torch.float64 if dtype == np.float64 else torch.float32, device="cuda")
-            handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, A, n, 0.0, Cm, m, Cm, m)
-            outs.append((host(Cm), handle.last_kernel()))
-        handle.set_option("geam.variant", 0)
-        assert outs[0][1].startswith("geam_transpose_tma") and outs[1][1].startswith("geam_tile")
-        assert np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8))
+        try:
+            for sel, order, upc in ((0, 0, 0), (2, 1, 0), (2, 0, 2), (1, 0, 0), (3, 0, 0)):
+                handle.set_option("geam.transpose", sel)
+                handle.set_option("geam.order", order)
+                handle.set_option("geam.upc", upc)
+                Cm = torch.full((m * n,), float("nan"), dtype=torch.float64 if dtype == np.float64 else torch.float32, device="cuda")
+                handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, A, n, 0.0, Cm, m, Cm, m)
+                outs.append((host(Cm), handle.last_kernel()))
+        finally:
+            for key in ("geam.transpose", "geam.order", "geam.upc"):
+                handle.set_option(key, 0)
+        assert [o[1].rsplit("_v16", 2)[0] for o in outs] == ["geam_transpose_reg"] * 3 + ["geam_transpose_tma", "geam_tile_tn"], [o[1] for o in outs]
+        for o in outs[1:]:
+            assert np.array_equal(outs[0][0].view(np.uint8), o[0].view(np.uint8)), o[1]
         assert np.array_equal(outs[0][0].reshape(n, m), host(A).reshape(m, n).T)
 
 
@@ -215,6 +222,15 @@ def test_geam_transpose_of_unaligned_source_into_padded_target(oracle, handle, d
     TMA-stored.  cp.async producers fill the TMA kernel's ring; bit-exact against the oracle for move (beta = 0, NaN in the
     target) and accumulate, ragged edge tiles, an element-aligned base pointer, and against the all-TMA path."""
     ld_unit = 16 // np.dtype(dtype).itemsize
+    try:
+        for sel, cp_name, tma_name in ((0, "geam_transpose_reg_s_v16", "geam_transpose_reg_v16"), (1, "geam_transpose_cpasync_tma", "geam_transpose_tma")):
+            handle.set_option("geam.transpose", sel)
+            _unaligned_source_cases(oracle, handle, dtype, ld_unit, cp_name, tma_name)
+    finally:
+        handle.set_option("geam.transpose", 0)
+
+
+def _unaligned_source_cases(oracle, handle, dtype, ld_unit, cp_name, tma_name):
     for (m, n, lda_pad, beta, offset) in [(517, 300, 1, 0.0, 0), (300, 517, 0, 0.0, 0), (1024, 257, 0, -0.75, 0), (640, 512, 0, 0.0, 1),
                                           (2049, 1301, 0, 1.0, 0)]:
         ldc_pad = (-m) % 32 if offset == 0 else 0
@@ -225,7 +241,7 @@ def test_geam_transpose_of_unaligned_source_into_padded_target(oracle, handle, d
             C0 = np.full(ldc * n, np.nan, dtype=dtype)
             dA, dC = dev(A), dev(C0)
             handle.geam(dtype == np.float64, 1, 0, m, n, 1.0, dA.data_ptr() + A.itemsize, lda, 0.0, dC, ldc, dC, ldc)
-            assert handle.last_kernel() == "geam_transpose_cpasync_tma", handle.last_kernel()
+            assert handle.last_kernel().startswith(cp_name), handle.last_kernel()
             exp = C0.copy()
             oracle.geam(1, 0, m, n, dtype(1.0), A[1:], lda, dtype(0.0), exp, ldc, exp, ldc)
             assert np.array_equal(host(dC).view(np.uint8), exp.view(np.uint8))
@@ -233,13 +249,15 @@ def test_geam_transpose_of_unaligned_source_into_padded_target(oracle, handle, d
         assert (n + lda_pad) % ld_unit != 0
         _geam_case(oracle, handle, dtype, 1, 0, m, n, 1.0, beta, 80 + m, lda_pad=lda_pad, ldb_pad=ldc_pad, ldc_pad=ldc_pad, inplace=True,
                    nan_b=(beta == 0.0))
-        assert handle.last_kernel().startswith("geam_transpose_cpasync_tma"), handle.last_kernel()
+        assert handle.last_kernel().startswith(cp_name[:-4] if "reg" in cp_name else cp_name), handle.last_kernel()
     # a row count that is not a multiple of 16 B on the all-TMA path: the bulk store clips at 16 B granularity, so the last
     # rows are stored by the transposers (this wrote row m of the padded target before)
     for (m, beta) in [(517, 0.0), (519, 0.5), (513, -1.0)]:
         pad = (-m) % 32
         _geam_case(oracle, handle, dtype, 1, 0, m, 300, 1.0, beta, 95 + m, ldb_pad=pad, ldc_pad=pad, inplace=True, nan_b=(beta == 0.0))
-        assert handle.last_kernel().startswith("geam_transpose_tma"), handle.last_kernel()
+        assert handle.last_kernel().startswith(tma_name), handle.last_kernel()
+    if "reg" in cp_name:
+        return
     # the producers against the TMA loads on a source both can address
     m, n = 1000, 1100
     A = dev(oracle.fill(n * m, 5, dtype))
@@ -275,7 +293,7 @@ def test_stream_binding_and_introspection(handle):
     torch.cuda.synchronize()
     h2.geam(True, 1, 0, 32, 32, 1.0, x, 32, 0.0, y, 32, y, 32)
     s.synchronize()
-    assert h2.launch_count() == n0 + 1 and h2.last_kernel().startswith("geam_tile")
+    assert h2.launch_count() == n0 + 1 and h2.last_kernel().startswith("geam_transpose_reg")
     assert torch.equal(x, y)
     h2.close()
 
@@ -507,14 +525,32 @@ def test_sgemm_tcgen05_3xtf32(oracle, handle, ta, tb, presplit):
         handle.set_option("sgemm.presplit", 1)
 
 
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_sgemm_tcgen05_pads_an_op_a_tma_cannot_address(oracle, handle, ta, tb):
+    """ld not a multiple of 4 floats / base 4 bytes off: op(A) is copied once into a 16 B-aligned buffer of the handle and
+    the tensor-core kernel runs on the copy (before: the FP32 SIMT fallback); B goes through the pre-split pass."""
+    for (m, n, k, lda_pad, offset) in [(300, 128, 96, 1, 0), (517, 257, 130, 3, 1), (1024, 64, 520, 2, 0), (129, 640, 33, 0, 1)]:
+        ar = k if ta else m
+        pad_a = (-ar) % 4 + lda_pad if lda_pad else (-ar) % 4
+        _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.25, -0.5, 1300 + m + k, lda_pad=pad_a, ldb_pad=1, ldc_pad=2, offset=offset)
+        name = handle.last_kernel()
+        unaligned = offset % 4 != 0 or (ar + pad_a) % 4 != 0
+        assert name.startswith("sgemm_tcgen05") and name.endswith("_padA") == unaligned, name
+    # too thin to pay for the extra pass over A: the FP32 kernel
+    _gemm_case(oracle, handle, np.float32, ta, tb, 300, 48, 96, 1.0, 0.0, 1399, lda_pad=1)
+    assert handle.last_kernel().startswith("sgemm_simt"), handle.last_kernel()
+
+
 def test_sgemm_tcgen05_rejects_what_tma_cannot_address(handle):
     handle.set_option("sgemm.variant", 2)
+    handle.set_option("sgemm.pad_a", 0)
     try:
         x = torch.zeros(70 * 70 + 8, dtype=torch.float32, device="cuda")
         assert handle.gemm(False, 0, 0, 70, 45, 62, 1.0, x, 70, x, 62, 0.0, x, 70, check=False) == 15  # ld = 70: not a multiple of 4
         assert handle.gemm(False, 0, 0, 64, 64, 64, 1.0, x.data_ptr() + 4, 64, x, 64, 0.0, x, 64, check=False) == 15  # 4 B aligned base
     finally:
         handle.set_option("sgemm.variant", 0)
+        handle.set_option("sgemm.pad_a", 1)
 
 
 def test_sgemm_accuracy_is_fp32_class_not_tf32_class(oracle, handle):

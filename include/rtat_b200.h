@@ -112,8 +112,9 @@ int rtat_b200_ssyrk(rtat_b200_handle_t handle, int uplo, int trans, int n, int k
 /* ---- TRSM:  op(A) X = alpha B (side LEFT) or X op(A) = alpha B (side RIGHT), X overwrites B   (replaces
  *      cublasDtrsm / cublasStrsm) ------------------------------------------------------------------
  * B is m x n; A is triangular (`uplo`), m x m for LEFT, n x n for RIGHT; only that triangle is read, and not its
- * diagonal when diag == UNIT.  alpha == 0 zeroes B without reading A.  Recursive blocked substitution whose
- * updates run in the GEMM kernels above (trsm.cu); no inverted diagonal blocks, true divisions. */
+ * diagonal when diag == UNIT.  alpha == 0 zeroes B without reading A.  Recursive blocked solve whose updates run in
+ * the GEMM kernels above (trsm.cu).  Only the 32 x 32 diagonal sub-blocks are inverted (one pre-pass per call, by
+ * substitution on the identity) and applied as small products; everything larger is substitution. */
 int rtat_b200_dtrsm(rtat_b200_handle_t handle, int side, int uplo, int trans, int diag, int m, int n,
                     const double *alpha, const double *A, int lda, double *B, int ldb);
 int rtat_b200_strsm(rtat_b200_handle_t handle, int side, int uplo, int trans, int diag, int m, int n,
@@ -135,10 +136,18 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *     dgemm.tile [0]            128 / 64: force the tile configuration of the persistent DGEMM
  *     dgemm.streamk [1]         0: data-parallel schedule only
  *     dgemm.tma3d [1]           0: eight 2-D TMA boxes per M/N-contiguous operand stage instead of one 3-D box
+ *     dgemm.peel [1]            0: keep remainders of 1..16 rows / columns in the 128x128 launch instead of a second
+ *                               launch on 64x64 tiles
+ *     dgemm.prefetch_c [1]      0: beta != 0 without the L2 prefetch of the C tile at the start of its main loop
  *     dgemm.l2_hints [0]        1: evict_last / evict_first on the A / B loads (measured: more DRAM traffic)
  *     dgemm.force_unaligned [0] 1: cp.async producers even when TMA could address the operands
  *     sgemm.presplit [1]        0: split op(B) into big / small TF32 parts per tile instead of once per call
- *     geam.force_cpasync [0]    1: cp.async producers in the transposing geam even for a TMA-addressable source
+ *     sgemm.pair [1]            0: single-CTA tcgen05 kernel instead of CTA pairs (cta_group::2)
+ *     sgemm.pad_a [1]           0: an op(A) TMA cannot address goes to the FP32 SIMT kernel instead of an aligned copy
+ *     geam.transpose [0]        transposing geam: 1 = TMA pipeline, 2 = register-blocked kernel (the default choice),
+ *                               3 = scalar tile kernel; geam.order = 1 / geam.upc = 2: CTA order / tile height of kernel 2
+ *     geam.persistent [0]       1: grid-stride streaming copies on 8 CTAs per SM instead of one chunk per CTA
+ *     geam.force_cpasync [0]    1: cp.async producers in the TMA transposer even for a TMA-addressable source
  *     geam.tune, geam.rounding  launch-shape and rounding experiments of geam (see csrc/geam.cu)
  *     trsm.base [0]             diagonal-block size of the recursive TRSM (0 = 128)
  *     host.panels, host.lead    override the schedule of the host-buffer entry points; host.trace = 1 prints

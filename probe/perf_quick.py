@@ -101,6 +101,29 @@ if which == "beta":
                 ms = timeit(lambda: h.gemm(True, ta, tb, m, n, k, 1.0, A, ar, B, br, beta, Cm, m))
                 print(f"{name:30s} beta={beta} prefetch_c={pf} {h.last_kernel():36s} {ms:9.3f} ms {2.0*m*n*k/ms*1e-9:8.2f} TFLOP/s", flush=True)
     h.set_option("dgemm.prefetch_c", 1)
+if which == "c3pad":
+    # config 3 after the explicit pad (what plan ..NPPN hands the multiply): A 4097 x 2049 ld 4128, B 3001 x 2049 ld 3008
+    m, n, k = 4097, 3001, 2049
+    A = torch.empty(4128 * k, dtype=torch.float64, device="cuda"); h.fill_uniform(A, 1)
+    B = torch.empty(3008 * k, dtype=torch.float64, device="cuda"); h.fill_uniform(B, 2)
+    Cm = torch.empty(m * n, dtype=torch.float64, device="cuda")
+    for tile in (0, 64, 128):
+        for peel in (1, 0):
+            h.set_option("dgemm.tile", tile); h.set_option("dgemm.peel", peel)
+            ms = timeit(lambda: h.gemm(True, 0, 1, m, n, k, 1.0, A, 4128, B, 3008, 0.0, Cm, m))
+            print(f"C3 padded NT tile={tile} peel={peel} {h.last_kernel():52s} {ms:9.4f} ms {2.0*m*n*k/ms*1e-9:8.2f} TFLOP/s", flush=True)
+    h.set_option("dgemm.tile", 0); h.set_option("dgemm.peel", 1)
+    for name, ta, tb, mm, nn, kk in [("NN 8193x8192x4096", 0, 0, 8193, 8192, 4096), ("TN 4100x4104x4096", 1, 0, 4100, 4104, 4096), ("NN 8200^2 x 2048", 0, 0, 8200, 8200, 2048)]:
+        ar, ac = (kk, mm) if ta else (mm, kk)
+        ar2 = ar + (ar % 2)
+        A = torch.empty(ar2 * ac, dtype=torch.float64, device="cuda"); h.fill_uniform(A, 1)
+        B = torch.empty(kk * nn, dtype=torch.float64, device="cuda"); h.fill_uniform(B, 2)
+        Cm = torch.empty(mm * nn, dtype=torch.float64, device="cuda")
+        for peel in (1, 0):
+            h.set_option("dgemm.peel", peel)
+            ms = timeit(lambda: h.gemm(True, ta, tb, mm, nn, kk, 1.0, A, ar2, B, kk, 0.0, Cm, mm))
+            print(f"{name:24s} peel={peel} {h.last_kernel():52s} {ms:9.4f} ms {2.0*mm*nn*kk/ms*1e-9:8.2f} TFLOP/s", flush=True)
+    h.set_option("dgemm.peel", 1)
 if which == "geam_tune":
     for t in range(7):
         h.set_option("geam.tune", t)

@@ -81,6 +81,7 @@ int rtat_b200_create(rtat_b200_handle_t *handle) {
   if (!h) return RTAT_B200_STATUS_ALLOC_FAILED;
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
+  h->l2_bytes = (size_t)prop.l2CacheSize;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
   h->stream = nullptr;  // legacy default stream until set_stream, as with cuBLAS

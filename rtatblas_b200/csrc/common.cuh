@@ -11,6 +11,7 @@
 struct rtat_b200_context {
   int device = 0;
   int sm_count = 0;
+  size_t l2_bytes = 0;
   int cc_major = 0, cc_minor = 0;
   cudaStream_t stream = nullptr;
   // library-owned device arena: stream-K partial tiles, pre-split operands, host-entry staging

@@ -88,7 +88,9 @@ struct Params {
   // GB, L2 hit rate 78.9 -> 75.7 %, time unchanged (DRAM is at 4 % of its bandwidth either way): the CTAs that share a B
   // panel drift apart in k, and an evict_first line is gone before the laggard asks for it.
   unsigned long long l2_a, l2_b;
-  int a_3d, b_3d;  // the operand's map is the 3-D view (see tma_load_3d)
+  // rows of op(A) / columns of op(B) the operand's 3-D map covers (see tma_load_3d; 0 = no 3-D map): a tile wholly below
+  // the limit is ONE box per stage, the ragged last tile row / column takes the 2-D boxes
+  int a_3d, b_3d;
   int prefetch_c;  // beta != 0: consumers prefetch their part of the C tile into L2 when the tile starts (option dgemm.prefetch_c)
 };
 
@@ -349,7 +351,8 @@ __device__ __forceinline__ void issue_operand_cpasync(uint32_t s, const double *
 
 template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
 __global__ void __launch_bounds__((Cfg::CONSUMER_WARPS + ((USE_TMA && !Cfg::SPLIT_REGS) ? 1 : CPASYNC_PRODUCER_WARPS)) * 32, Cfg::CTAS_PER_SM)
-dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA3,
+                const __grid_constant__ CUtensorMap mapB3, const Params p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr bool KCA = TA;    // op(A)(m,k): stored k x m when transposed => k contiguous
@@ -424,16 +427,16 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int k0 = kt * BK;
             if (KCA) {
               tma_load_2d(sA, &mapA, k0, m0, full, p.l2_a);
-            } else if (p.a_3d) {
-              tma_load_3d(sA, &mapA, 0, k0, m0 / 16, full, p.l2_a);
+            } else if (m0 + BM <= p.a_3d) {
+              tma_load_3d(sA, &mapA3, 0, k0, m0 / 16, full, p.l2_a);
             } else {
 #pragma unroll
               for (int b = 0; b < BM / 16; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 16 * b, k0, full, p.l2_a);
             }
             if (KCB) {
               tma_load_2d(sB, &mapB, k0, n0, full, p.l2_b);
-            } else if (p.b_3d) {
-              tma_load_3d(sB, &mapB, 0, k0, n0 / 16, full, p.l2_b);
+            } else if (n0 + BN <= p.b_3d) {
+              tma_load_3d(sB, &mapB3, 0, k0, n0 / 16, full, p.l2_b);
             } else {
 #pragma unroll
               for (int b = 0; b < BN / 16; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 16 * b, k0, full, p.l2_b);
@@ -698,7 +701,7 @@ static bool make_map_3d(CUtensorMap *map, const double *base, uint64_t rows, uin
 }
 
 template <class Cfg, bool TA, bool TB, bool USE_TMA, bool TRI = false>
-static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap &ma, const CUtensorMap &mb, const char *name) {
+static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtensorMap (&maps)[4], const char *name) {
   auto kern = dgemm_ws_kernel<Cfg, TA, TB, USE_TMA, TRI>;
   constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
@@ -706,7 +709,7 @@ static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtenso
   if (int st = configure_dynamic_smem(kern, SMEM_BYTES, h->device, configured)) return st;
   // with setmaxnreg the producer warpgroup is always complete
   int threads = (CONSUMER_WARPS + ((USE_TMA && !Cfg::SPLIT_REGS) ? 1 : CPASYNC_PRODUCER_WARPS)) * 32;
-  kern<<<grid, threads, SMEM_BYTES, h->stream>>>(ma, mb, p);
+  kern<<<grid, threads, SMEM_BYTES, h->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   return check_launch(h, name);
 }
 
@@ -846,16 +849,16 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   const bool hints = !tri && opt(h, "dgemm.l2_hints", 0) != 0;
   p.l2_a = hints ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   p.l2_b = hints ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-  CUtensorMap ma, mb;
-  memset(&ma, 0, sizeof ma);
-  memset(&mb, 0, sizeof mb);
+  CUtensorMap maps[4];  // A, B (2-D boxes) and their 3-D views
+  memset(maps, 0, sizeof maps);
   if (use_tma) {
-    // M/N-contiguous operands: one 3-D box per stage instead of BMN / 16 two-dimensional ones when the extent allows
+    // M/N-contiguous operands: one 3-D box per stage instead of BMN / 16 two-dimensional ones for every tile that lies
+    // wholly inside the multiple of 16 the view can cover; only the ragged last tile row / column uses the 2-D boxes
     const bool box3 = opt(h, "dgemm.tma3d", 1) != 0;
-    p.a_3d = !ta && box3 && m % 16 == 0 && make_map_3d(&ma, A, m, k, lda, BK, BM);
-    p.b_3d = tb && box3 && n % 16 == 0 && make_map_3d(&mb, B, n, k, ldb, BK, BN);
-    bool ok = p.a_3d || (ta ? make_map(&ma, A, k, m, lda, BK, BM) : make_map(&ma, A, m, k, lda, 16, BK));
-    ok = ok && (p.b_3d || (!tb ? make_map(&mb, B, k, n, ldb, BK, BN) : make_map(&mb, B, n, k, ldb, 16, BK)));
+    if (!ta && box3 && m / 16 * 16 >= BM && make_map_3d(&maps[2], A, m / 16 * 16, k, lda, BK, BM)) p.a_3d = m / 16 * 16;
+    if (tb && box3 && n / 16 * 16 >= BN && make_map_3d(&maps[3], B, n / 16 * 16, k, ldb, BK, BN)) p.b_3d = n / 16 * 16;
+    bool ok = ta ? make_map(&maps[0], A, k, m, lda, BK, BM) : make_map(&maps[0], A, m, k, lda, 16, BK);
+    ok = ok && (!tb ? make_map(&maps[1], B, k, n, ldb, BK, BN) : make_map(&maps[1], B, n, k, ldb, 16, BK));
     if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;  // descriptor out of range (dims >= 2^32): caller falls back
   }
   // kernel name reported through rtat_b200_last_kernel: dgemm_ws_dmma_<tile>_{tma|cpasync8}[_streamk]
@@ -863,11 +866,11 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   snprintf(name, sizeof name, "%s_ws_dmma_%s_%s%s", tri ? "dsyrk" : "dgemm", tile_name, use_tma ? "tma" : "cpasync8", sk_tiles ? "_streamk" : "");
   if (tri) {
     if (ta)
-      return use_tma ? launch<Cfg, true, false, true, true>(h, p, grid, ma, mb, name) : launch<Cfg, true, false, false, true>(h, p, grid, ma, mb, name);
-    return use_tma ? launch<Cfg, false, true, true, true>(h, p, grid, ma, mb, name) : launch<Cfg, false, true, false, true>(h, p, grid, ma, mb, name);
+      return use_tma ? launch<Cfg, true, false, true, true>(h, p, grid, maps, name) : launch<Cfg, true, false, false, true>(h, p, grid, maps, name);
+    return use_tma ? launch<Cfg, false, true, true, true>(h, p, grid, maps, name) : launch<Cfg, false, true, false, true>(h, p, grid, maps, name);
   }
 #define RTAT_WS(TA_, TB_) \
-  (use_tma ? launch<Cfg, TA_, TB_, true>(h, p, grid, ma, mb, name) : launch<Cfg, TA_, TB_, false>(h, p, grid, ma, mb, name))
+  (use_tma ? launch<Cfg, TA_, TB_, true>(h, p, grid, maps, name) : launch<Cfg, TA_, TB_, false>(h, p, grid, maps, name))
   if (!ta && !tb) return RTAT_WS(false, false);
   if (ta && !tb) return RTAT_WS(true, false);
   if (!ta && tb) return RTAT_WS(false, true);
@@ -879,32 +882,67 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
 // with the opposite op; only tiles touching the triangle are scheduled and the diagonal tiles are masked).
 int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
              const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg, int tri) {
+  // Thin remainders are peeled off.  A 128x128 tile with only a few valid rows (or columns) costs a whole tile: its
+  // consumers skip work at warp granularity only (they sit at the register cap), and with m % 128 <= PEEL_MAX the rows
+  // all belong to the same two of the eight warps' M-slice, i.e. to two busy warps on two of the four sub-partitions.  Config 3
+  // (m = 4097) spent 24 of its 792 tile times on ONE row of C.  Such a strip goes to a second, small launch on 64x64
+  // tiles (whose consumers skip single 8-row blocks) and the 128x128 launch sees a multiple of 128.
+  constexpr int PEEL_MAX = 16;
+  auto peelable = [&](int x) { return !tri && opt(h, "dgemm.peel", 1) != 0 && x % 128 > 0 && x % 128 <= PEEL_MAX && x >= 512; };
+  const int m_main = peelable(m) ? m - m % 128 : m, n_main = peelable(n) ? n - n % 128 : n;
+  const bool peel = m_main != m || n_main != n;
   if (tile_cfg == 0) {
     // Estimated cost = padded tile area x waves.  128x128 tiles are the more efficient steady state
     // (98 % vs ~94 % of the DMMA pipe), 64x64 tiles waste less on ragged edges and keep stream-K fix-ups
     // four times smaller, which decides small problems.
     // ragged tiles are charged what their busiest sub-partition multiplies (tile_cost)
-    auto padded = [&](int bm) {
-      double tm = (m + bm - 1) / bm, tn = (n + bm - 1) / bm;
+    auto padded = [&](int bm, int mm, int nn) {
+      double tm = (mm + bm - 1) / bm, tn = (nn + bm - 1) / bm;
       if (tri) return tm * (tm + 1) / 2 * bm * bm;
       const bool amn = !ta;
       auto cost = [&](int rows, int cols) { return bm == 128 ? tile_cost<ws::Cfg128>(amn, rows, cols) : tile_cost<ws::Cfg64>(amn, rows, cols); };
-      double tmf = m / bm, tnf = n / bm, sixteenths = 16.0 * tmf * tnf;
-      if (n % bm) sixteenths += tmf * cost(0, n % bm);
-      if (m % bm) sixteenths += tnf * cost(m % bm, 0);
-      if (m % bm && n % bm) sixteenths += cost(m % bm, n % bm);
+      double tmf = mm / bm, tnf = nn / bm, sixteenths = 16.0 * tmf * tnf;
+      if (nn % bm) sixteenths += tmf * cost(0, nn % bm);
+      if (mm % bm) sixteenths += tnf * cost(mm % bm, 0);
+      if (mm % bm && nn % bm) sixteenths += cost(mm % bm, nn % bm);
       return sixteenths / 16.0 * bm * bm;
     };
     // measured steady-state efficiencies: TMA producers 0.985 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
     const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
-    double t128 = padded(128) / (tma ? 0.985 : 0.92), t64 = padded(64) / (tma ? 0.96 : 0.85);
+    // the peeled strips ride along at the 64x64 rate plus ~5 us of fixed cost per launch (as C area: t x rate / 2k)
+    const double launch_area = 5e-6 * 36e12 / (2.0 * (k > 0 ? k : 1));
+    double strips = peel ? (padded(64, m - m_main, n) + padded(64, m_main, n - n_main)) / (tma ? 0.96 : 0.85) +
+                               launch_area * ((m_main != m) + (n_main != n))
+                         : 0.0;
+    double t128 = padded(128, m_main, n_main) / (tma ? 0.985 : 0.92) + strips, t64 = padded(64, m, n) / (tma ? 0.96 : 0.85);
     long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16) / (tri ? 2 : 1);
     bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
+    // 64x64 tiles pull twice the operand bytes through L2; when A and B fit in L2 that costs nothing and the two
+    // estimates are closer than their error, so a peeled 128x128 schedule has to win by 3 % (config 3 inside the planner,
+    // operands hot in L2 from the pad pass: 64x64 1.453 ms, 128x128 + strip 1.470; cold: 1.527 against 1.496)
+    const bool l2_resident = 8.0 * ((double)m * k + (double)k * n) < 0.95 * (double)h->l2_bytes;
+    if (peel && l2_resident) t128 *= 1.03;
     tile_cfg = (small || t64 < t128) ? 64 : 128;
   }
   if (tile_cfg == 64)
     return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);
-  return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
+  if (!peel) return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
+  int st = run_cfg<ws::Cfg128>(h, ta, tb, m_main, n_main, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
+  if (st) return st;
+  static thread_local char name[112];
+  snprintf(name, sizeof name, "%s+strips64", h->last_kernel);
+  if (m_main != m) {  // rows [m_main, m), all columns
+    const double *As = ta ? A + (size_t)m_main * lda : A + m_main;
+    st = run_cfg<ws::Cfg64>(h, ta, tb, m - m_main, n, k, alpha, As, lda, B, ldb, beta, C + m_main, ldc, allow_tma, "64x64x16", 0);
+    if (st) return st;
+  }
+  if (n_main != n) {  // columns [n_main, n) of the rows the main launch covered
+    const double *Bs = tb ? B + n_main : B + (size_t)n_main * ldb;
+    st = run_cfg<ws::Cfg64>(h, ta, tb, m_main, n - n_main, k, alpha, A, lda, Bs, ldb, beta, C + (size_t)n_main * ldc, ldc, allow_tma, "64x64x16", 0);
+    if (st) return st;
+  }
+  h->last_kernel = name;
+  return RTAT_B200_STATUS_SUCCESS;
 }
 
 }  // namespace rtat_b200

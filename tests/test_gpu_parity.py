@@ -401,13 +401,14 @@ def test_dgemm_config5_column_block(handle):
     _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)
 
 
-@pytest.mark.parametrize("tile", [64, 128])
-def test_dgemm_ragged_tiles_every_residue_class(handle, tile):
+@pytest.mark.parametrize("tile,peel", [(64, 1), (128, 1), (128, 0)])
+def test_dgemm_ragged_tiles_every_residue_class(handle, tile, peel):
     """The consumers of a ragged tile skip the DMMA blocks (64x64 tiles) or whole warps (128x128) that lie outside C, and the
     ragged tiles are scheduled after the full ones: residues on either side of every 8 / 16 / 32 / 64 boundary, both operand
     orientations (8-row blocks for a K-contiguous operand, pairs of blocks for an M/N-contiguous one), k long enough for
     the stream-K split (kt >= 8); C starts as NaN so an element nobody wrote is caught."""
     handle.set_option("dgemm.tile", tile)
+    handle.set_option("dgemm.peel", peel)  # 128x128 tiles: remainders of <= 16 rows / columns go to a second launch on 64x64 tiles
     try:
         res = [1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 57, 63, 65, 100, 127]
         for i, rm in enumerate(res):
@@ -419,6 +420,26 @@ def test_dgemm_ragged_tiles_every_residue_class(handle, tile):
         _full_size_vs_cublas(handle, np.float64, 1, 0, tile - 3, tile - 5, 300, 9302)
     finally:
         handle.set_option("dgemm.tile", 0)
+        handle.set_option("dgemm.peel", 1)
+
+
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_dgemm_thin_remainders_are_peeled_into_a_second_launch(oracle, handle, ta, tb):
+    """m % 128 or n % 128 in 1..16 on 128x128 tiles: the main launch covers the multiple of 128, 64x64-tile launches the
+    row strip (all columns) and the column strip (main rows); every element written once, alpha / beta honoured in each
+    piece, padding of C untouched, and the same result as the unpeeled kernel to within the bound."""
+    handle.set_option("dgemm.tile", 128)
+    try:
+        for (m, n, k, beta) in [(641, 528, 200, 0.0), (1025, 643, 96, -0.5), (520, 1033, 130, 1.0), (513, 512, 64, 0.0)]:
+            _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9500 + m, ldc_pad=3, nan_c=(beta == 0.0))
+            assert handle.last_kernel().endswith("+strips64"), handle.last_kernel()
+            handle.set_option("dgemm.peel", 0)
+            _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9500 + m, ldc_pad=3, nan_c=(beta == 0.0))
+            assert "strips" not in handle.last_kernel()
+            handle.set_option("dgemm.peel", 1)
+    finally:
+        handle.set_option("dgemm.tile", 0)
+        handle.set_option("dgemm.peel", 1)
 
 
 def test_dgemm_l2_eviction_hints_do_not_change_results(handle):

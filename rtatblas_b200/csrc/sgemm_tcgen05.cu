@@ -294,7 +294,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           const int k0 = kb * BK;
           if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
           else
-            for (int b = 0; b < BM / 32; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 32 * b, k0, full);
+            tma_load_2d(sA, &mapA, m0, k0, full);  // one box: 32 k-rows of 128 consecutive m (512 contiguous bytes each)
           if (KCB) tma_load_2d(sB, &mapB, k0, n0, full);
           else
             for (int b = 0; b < BN / 32; b++) tma_load_2d(sB + b * (BK * 128), &mapB, n0 + 32 * b, k0, full);
@@ -366,11 +366,11 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
           }
         } else {
-          // M-major tile: box (t / 32) holds [32 k][32 m] unswizzled; a warp reads one 128 B k-row per load
+          // M-major tile: [32 k][128 m] unswizzled (one TMA box); a warp reads 128 contiguous bytes of one k-row per load
 #pragma unroll
           for (int kk = 0; kk < 32; kk++) {
             float x;
-            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + (t >> 5) * (BK * 128) + kk * 128 + (t & 31) * 4));
+            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + kk * (BM * 4) + t * 4));
             big[kk] = to_tf32(x);
             small[kk] = to_tf32(x - __uint_as_float(big[kk]));
           }
@@ -573,7 +573,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const int k0 = kb * BK;
           if (KCA) tma_load_2d(sA, &mapA, k0, m0, full);
           else
-            for (int b = 0; b < BM / 32; b++) tma_load_2d(sA + b * (BK * 128), &mapA, m0 + 32 * b, k0, full);
+            tma_load_2d(sA, &mapA, m0, k0, full);  // one box: 32 k-rows of 128 consecutive m (512 contiguous bytes each)
           if (KCB) {
             tma_load_2d(sB, &mapB, k0, nb0, full);
             tma_load_2d(sBs, &mapBs, k0, nb0, full);
@@ -655,7 +655,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 #pragma unroll
           for (int kk = 0; kk < 32; kk++) {
             float x;
-            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + (t >> 5) * (BK * 128) + kk * 128 + (t & 31) * 4));
+            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + kk * (BM * 4) + t * 4));
             big[kk] = to_tf32(x);
             small[kk] = to_tf32(x - __uint_as_float(big[kk]));
           }
@@ -872,7 +872,7 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   const bool use_pair = !tri && presplit && p.tiles_m >= 2 && opt(h, "sgemm.pair", 1) != 0;
   const int bn_box = use_pair ? BN / 2 : BN;
   // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle
-  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+  bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
   ok = ok && (!tb ? make_map(&mb, Bbig, k, n, ldb_eff, BK, bn_box, kmaj) : make_map(&mb, Bbig, n, k, ldb_eff, 32, BK, mnmaj));
   ok = ok && (!tb ? make_map(&mbs, Bsmall, k, n, ldb_eff, BK, bn_box, kmaj) : make_map(&mbs, Bsmall, n, k, ldb_eff, 32, BK, mnmaj));
   if (!ok) return RTAT_B200_STATUS_NOT_SUPPORTED;

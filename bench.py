@@ -33,6 +33,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+DEFAULT_PREFERENCE = 0.02
+
 CONFIGS = {
     # name: (dtype, transA, transB, m, n, k)
     "c1": ("double", "N", "N", 1024, 1024, 1024),
@@ -411,6 +413,10 @@ def main():
         method = "gemm_pad" if name == "c3" else "gemm"  # config 3 is the one where pad/copy plans matter: 64-plan space
         planner = rt.Planner(method, dtype)
         planner.set_tests_until_converge(samples_per_plan)
+        # one to three event samples per plan jitter by a per cent or two; a plan that spends extra passes and workspace has
+        # to beat the default (fully fused) plan by more than that to displace it (Planning_System::set_default_preference,
+        # off in the library by default, where the reference's strict minimum of the means is kept)
+        planner.set_default_preference(DEFAULT_PREFERENCE)
         ar, ac = (k, m) if ta else (m, k)
         br, bc = (n, k) if tb else (k, n)
         A = torch.empty(ar * ac, dtype=tdt, device="cuda")
@@ -548,6 +554,7 @@ def main():
                 "config": {"workload": workload_string(cfg_name, cfg)},
                 "details": {"api": "Planning_System::create_plan + execute (rtat.h surface) -> MatrixOp tree -> rtat_b200_* C ABI", "plan": head["plan"],
                             "plan_meaning": "NNN = transpose/pad fused into the GEMM's loads; T.. / ...P.. = explicit MatrixMove pass first",
+                            "planner_default_preference": DEFAULT_PREFERENCE,
                             "best_ms_per_plan": head["best_ms_per_plan"], "parallelism": "one GPU", "l2_policy": head["l2_policy"],
                             "pct_of_fp64_dmma_peak": round(100 * head["value"] / DMMA_PEAK_TFLOPS, 2) if dbl else None},
                 "roofline": head["roofline"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "kernel": head["kernel"],

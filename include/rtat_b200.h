@@ -165,7 +165,7 @@ uint64_t rtat_b200_launch_count(rtat_b200_handle_t handle);
  * n = this rank's column count.  opt_panels / opt_lead as the options host.panels / host.lead (0 = automatic).
  * out = {blocks, lead, npanels, nb, col0[blocks], cols[blocks], k0[npanels], kc[npanels]}: column blocks of op(B) / C,
  * how many leading ones take the K-panel phase, and the K-panels of A.  Returns the number of ints written, -1 on a bad
- * argument or when cap is too small (44 always suffices). */
+ * argument or when cap is too small (80 always suffices). */
 int rtat_b200_host_schedule(int elem_size, int transa, int m, int n, int k, int lda, int world, int opt_panels, int opt_lead, int *out,
                             int cap);
 

@@ -37,8 +37,8 @@ def lib():
 def host_schedule(elem_size, transa, m, n, k, lda, world=0, panels=0, lead=0):
     """The schedule the host-buffer entry points would use (rtat_b200_host_schedule; pure host arithmetic, no GPU needed):
     dict with the column blocks [(col0, cols)], how many leading ones take the K-panel phase, and the K-panels [(k0, kc)]."""
-    out = (C.c_int * 64)()
-    got = lib().rtat_b200_host_schedule(elem_size, transa, m, n, k, lda, world, panels, lead, out, 64)
+    out = (C.c_int * 128)()
+    got = lib().rtat_b200_host_schedule(elem_size, transa, m, n, k, lda, world, panels, lead, out, 128)
     if got < 0:
         raise RtatError("rtat_b200_host_schedule: bad argument")
     blocks, nlead, npanels, nb = out[0], out[1], out[2], out[3]

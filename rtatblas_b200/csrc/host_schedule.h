@@ -15,9 +15,10 @@ namespace rtat_b200 {
 
 struct HostSchedule {
   static constexpr int MAX_BLOCKS = 8, MAX_PANELS = 8;
+  static constexpr int BLOCK_CAP = MAX_BLOCKS + 6, PANEL_CAP = 2 * MAX_PANELS + 8;  // with the tapered tail / head
   int blocks = 0, lead = 0, npanels = 0, nb = 0;
-  int col0[MAX_BLOCKS + 2] = {}, cols[MAX_BLOCKS + 2] = {};  // column blocks of op(B) / C
-  int k0s[MAX_PANELS + 2] = {}, kcs[MAX_PANELS + 2] = {};    // K-panels of A
+  int col0[BLOCK_CAP] = {}, cols[BLOCK_CAP] = {};  // column blocks of op(B) / C
+  int k0s[PANEL_CAP] = {}, kcs[PANEL_CAP] = {};    // K-panels of A
 };
 
 // elem: sizeof(T).  bytes_a: bytes of A as stored.  a_share: fraction of A that crosses this GPU's PCIe link, pcie_rate:
@@ -35,12 +36,17 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
     sc.col0[j] = j * nb;
     sc.cols[j] = (sc.col0[j] + nb > n) ? n - sc.col0[j] : nb;
   }
-  if (blocks > 1 && sc.cols[blocks - 1] >= 512) {
+  // The copy back of the last block is the one transfer nothing can hide.  Multi-GPU caller: the last block is halved.
+  // Single-GPU caller: it is tapered — halved again and again down to 256 columns (4096 -> 2048, 1024, 512, 256, 256) — each
+  // piece's copy back hides behind the next piece's product, which is still several times longer (config 5: the exposed
+  // tail goes from 537 MB to 67 MB, 10 ms to 1.3 ms).
+  while (blocks > 1 && sc.cols[blocks - 1] >= 512 && blocks < HostSchedule::BLOCK_CAP) {
     const int half = sc.cols[blocks - 1] / 2 / 128 * 128;
     sc.col0[blocks] = sc.col0[blocks - 1] + half;
     sc.cols[blocks] = sc.cols[blocks - 1] - half;
     sc.cols[blocks - 1] = half;
     blocks++;
+    if (multi) break;
   }
   int panels = 1, lead = 0;
   // The multi-GPU entry is collective: every rank must cut K into the SAME panels (the peers' "panel p has arrived" flags
@@ -62,6 +68,35 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
   }
   const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
   int npanels = 0;
+  // Head of the single-GPU schedule when the leading blocks' product is clearly longer than the panel's upload (growth
+  // = t_product / t_upload - 1 per k-row >= 0.25; config 5: 0.37): the first panel is what the GPU waits for, so it starts at
+  // 256 k and each panel may exceed the first by `growth` times everything uploaded before it — the largest step that never
+  // lets the product of panel p - 1 end before panel p has landed — until the regular width kp is reached (config 5: 1.5 ms
+  // instead of 12 ms before the first product starts, for seven more beta = 1 passes).  Balanced problems (config 2: lead is
+  // chosen so that product and upload take equally long, growth ~ 0) keep the halved first panel below.
+  double growth = 0.0;
+  if (!multi && panels > 1 && lead > 0 && opt_panels == 0) {
+    const double rate = elem == 8 ? 33e12 : 150e12;
+    const double lead_cols = double(nb) * lead;
+    const double t_up = (double(bytes_a) / k * a_share + double(elem) * lead_cols) / pcie_rate, t_mm = 2.0 * m * lead_cols / rate;
+    growth = t_mm / t_up - 1.0;
+  }
+  if (growth >= 0.25 && kp >= 1024) {
+    if (growth > 1.0) growth = 1.0;
+    int done = 0;
+    while (done < k && npanels < HostSchedule::PANEL_CAP - 1) {
+      int w = npanels == 0 ? 256 : int(256 + growth * done) / 16 * 16;
+      if (w > kp) w = kp;
+      if (done + w > k || npanels == HostSchedule::PANEL_CAP - 2) w = k - done;
+      sc.k0s[npanels] = done;
+      sc.kcs[npanels++] = w;
+      done += w;
+    }
+    sc.blocks = blocks;
+    sc.lead = lead;
+    sc.npanels = npanels;
+    return sc;
+  }
   for (int p0 = 0; p0 < k; p0 += kp) {
     sc.k0s[npanels] = p0;
     sc.kcs[npanels++] = p0 + kp > k ? k - p0 : kp;

@@ -18,14 +18,14 @@ def _check(sc, n, k):
         pos += cnt
     assert pos == n
     assert all(c0 % 128 == 0 for c0, _ in blocks)
-    assert 1 <= len(blocks) <= 9  # 8 blocks, the last one halved
+    assert 1 <= len(blocks) <= 14  # 8 blocks, the last one halved (multi-GPU caller) or tapered down to 256 columns
     # K-panels: contiguous, in order, cover [0, k); starts are multiples of 16 (the DGEMM's k-tile)
     pos = 0
     for k0, kc in panels:
         assert k0 == pos and kc > 0 and k0 % 16 == 0
         pos += kc
     assert pos == k
-    assert len(panels) <= 9  # 8 panels, the first one halved
+    assert len(panels) <= 24  # 8 panels, the first one halved — or a head that grows from 256 k to the regular width
     # the K-panel phase exists only with more than one panel, and then for at least one and at most all blocks
     if len(panels) == 1:
         assert lead == 0
@@ -56,11 +56,19 @@ def test_baseline_config_schedules_match_the_design_notes():
     # config 2 (8192^3, op TN): 8 K-panels of 1024 with the first one halved, 9 column blocks (the last of 8 halved), 4 leading
     sc = rt.host_schedule(8, 1, 8192, 8192, 8192, 8192)
     assert sc["panels"] == [(0, 512), (512, 512)] + [(1024 * i, 1024) for i in range(1, 8)]
-    assert [c for _, c in sc["blocks"]] == [1024] * 7 + [512, 512]
+    assert [c for _, c in sc["blocks"]] == [1024] * 7 + [512, 256, 256]   # tapered tail: only 256 columns' copy back is exposed
     assert sc["lead"] == 4
     # config 3 (4097 x 3001 x 2049, op NT): every block is a leading one (the transfer of A dominates)
     sc = rt.host_schedule(8, 0, 4097, 3001, 2049, 4097)
     assert sc["lead"] == len(sc["blocks"]) and len(sc["panels"]) == 3
+    # config 5 on one GPU: one leading block whose product is 1.4x its panel's upload -> a head growing from 256 k by 0.37 of
+    # what is already up to the regular 4096, and a tail tapered from 4096 columns down to 256
+    sc = rt.host_schedule(8, 0, 32768, 32768, 32768, 32768)
+    widths = [kc for _, kc in sc["panels"]]
+    assert sc["lead"] == 1 and widths[0] == 256 and widths[-2] == 4096 and max(widths) == 4096
+    assert all(b >= a for a, b in zip(widths[:-1], widths[1:-1] + [4096])) and len(widths) <= 20
+    assert all(w <= 256 + 0.38 * sum(widths[:i]) + 16 for i, w in enumerate(widths[:-1]))
+    assert [c for _, c in sc["blocks"]][-5:] == [2048, 1024, 512, 256, 256]
     # config 5 per rank (m = k = 32768, n = 32768 / world): the multi-GPU caller's margin on the leading blocks
     assert rt.host_schedule(8, 0, 32768, 16384, 32768, 32768, world=2)["lead"] == 1
     assert rt.host_schedule(8, 0, 32768, 8192, 32768, 32768, world=4)["lead"] == 2

@@ -123,6 +123,30 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
+// Split of one op(A) element for the tensor core: big = tf32(x) (round to nearest, ties away), small = x - big.
+// RTAT_SGEMM_FAST_SPLIT = 0: both through cvt.rna.tf32.f32, which ptxas expands to VIADD + LOP3 + FSETP + SEL each (the
+// NaN-preserving form) — 8 ALU instructions per element besides the FADD, ~350 issue slots per k-block for a split warp.
+// = 1: big = (bits + 0x1000) & ~0x1fff (the same value for every finite x, Inf included; only NaNs whose payload has
+// bits 12-22 all set come out wrong, and those are caught by small), small = x - big handed over UNROUNDED: the
+// tensor core ignores the 13 low mantissa bits of a tf32 operand, i.e. truncates small (relative error 2^-10 of a value
+// that is itself <= 2^-11 |x|: 2^-21 |x|, zero-mean, the size of the small * small term 3xTF32 drops anyway), and a NaN or
+// Inf in x makes small = NaN, which the truncation keeps a NaN.  3 instructions per element.
+// Measured (config 4 / 4096^3 TN / 8192^3 NT, CTA pairs): 0.598 -> 0.554 ms / 220 -> 243 / 215 -> 243 TFLOP/s, error
+// against the exact product unchanged to three digits (probe/sgemm_pair.py); the split warps were the latency between a
+// stage landing and its MMAs, and their ALU work counts against the power cap the kernel runs at.
+#ifndef RTAT_SGEMM_FAST_SPLIT
+#define RTAT_SGEMM_FAST_SPLIT 1
+#endif
+__device__ __forceinline__ void split_a(float x, uint32_t &big, uint32_t &small) {
+#if RTAT_SGEMM_FAST_SPLIT
+  big = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  small = __float_as_uint(x - __uint_as_float(big));
+#else
+  big = to_tf32(x);
+  small = to_tf32(x - __uint_as_float(big));
+#endif
+}
+
 // One lane of the (converged) warp, chosen by the hardware.  The issuing warps run their loops with all 32 lanes and
 // only issue under this predicate: every operand is then warp-uniform for ptxas (uniform registers, no per-instruction
 // election loops), which a `lane == 0` region does not give it.
@@ -361,8 +385,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              big[4 * c + e] = to_tf32(x[e]);
-              small[4 * c + e] = to_tf32(x[e] - __uint_as_float(big[4 * c + e]));
+              split_a(x[e], big[4 * c + e], small[4 * c + e]);
             }
           }
         } else {
@@ -371,8 +394,7 @@ sgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           for (int kk = 0; kk < 32; kk++) {
             float x;
             asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + kk * (BM * 4) + t * 4));
-            big[kk] = to_tf32(x);
-            small[kk] = to_tf32(x - __uint_as_float(big[kk]));
+            split_a(x, big[kk], small[kk]);
           }
         }
         const uint32_t ta = lane_base + TMEM_A0 + 64 * stage;
@@ -526,8 +548,17 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
   const int pair_id = blockIdx.x / 2, num_pairs = gridDim.x / 2;
-  // pair tiles: 256 rows x 128 columns, numbered down the columns of the tile grid; this CTA's half starts at row 128 * rank
-  const int pairs_m = (p.tiles_m + 1) / 2, num_pair_tiles = pairs_m * p.tiles_n;
+  // pair tiles: 256 rows x 128 columns, numbered down the columns of the tile grid; this CTA's half starts at row 128 * rank.
+  // SSYRK (p.tri): only the pair tiles that touch the triangle, pair row by pair row — columns 0 .. 2 I + 1 of pair row I
+  // for the lower triangle, 2 I .. tiles_n - 1 for the upper one.  The half tile on the far side of the diagonal (one per
+  // pair row) is multiplied and masked away by the epilogue: 1 / (tiles_m + 1) of the work.
+  const int pairs_m = (p.tiles_m + 1) / 2;
+  auto tri_count = [&](int I) { return p.tri == 1 ? min(2 * I + 2, p.tiles_n) : p.tiles_n - 2 * I; };
+  int num_pair_tiles = pairs_m * p.tiles_n;
+  if (p.tri) {
+    num_pair_tiles = 0;
+    for (int I = 0; I < pairs_m; I++) num_pair_tiles += tri_count(I);
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -552,6 +583,13 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
   auto origin = [&](int pt, int &m0, int &n0) {
+    if (p.tri) {
+      int I = 0;
+      for (int c = tri_count(0); pt >= c; c = tri_count(I)) { pt -= c; I++; }  // <= pairs_m steps, once per 256 x 128 tile
+      m0 = I * (2 * BM) + (int)rank * BM;
+      n0 = (p.tri == 1 ? pt : 2 * I + pt) * BN;
+      return;
+    }
     m0 = (pt % pairs_m) * (2 * BM) + (int)rank * BM;
     n0 = (pt / pairs_m) * BN;
   };
@@ -647,8 +685,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              big[4 * c + e] = to_tf32(x[e]);
-              small[4 * c + e] = to_tf32(x[e] - __uint_as_float(big[4 * c + e]));
+              split_a(x[e], big[4 * c + e], small[4 * c + e]);
             }
           }
         } else {
@@ -656,8 +693,7 @@ sgemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           for (int kk = 0; kk < 32; kk++) {
             float x;
             asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(sA + kk * (BM * 4) + t * 4));
-            big[kk] = to_tf32(x);
-            small[kk] = to_tf32(x - __uint_as_float(big[kk]));
+            split_a(x, big[kk], small[kk]);
           }
         }
         if (STAGES > TSLOTS && it >= TSLOTS) {
@@ -766,17 +802,22 @@ static int launch_pair(rtat_b200_context *h, const Params &p, const CUtensorMap 
   auto kern = pair::sgemm_tcgen05_pair_kernel<TA, TB>;
   static std::atomic<uint64_t> configured{0};  // per template instantiation
   if (int st = configure_dynamic_smem(kern, pair::SMEM_BYTES, h->device, configured)) return st;
-  const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n, max_pairs = h->sm_count / 2;
-  const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
+  const int pairs_m = (p.tiles_m + 1) / 2, max_pairs = h->sm_count / 2;
+  long long pair_tiles = (long long)pairs_m * p.tiles_n;
+  if (p.tri) {  // the pair tiles that touch the triangle (same count the kernel derives)
+    pair_tiles = 0;
+    for (int I = 0; I < pairs_m; I++) pair_tiles += p.tri == 1 ? std::min(2 * I + 2, p.tiles_n) : p.tiles_n - 2 * I;
+  }
+  const int grid = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
   kern<<<grid, NUM_THREADS, pair::SMEM_BYTES, h->stream>>>(ma, mb, mbs, p);
-  return check_launch(h, "sgemm_tcgen05_3xtf32_2cta_256x128x32_presplitB", 2);
+  return check_launch(h, p.tri ? "ssyrk_tcgen05_3xtf32_2cta_256x128x32_presplitB" : "sgemm_tcgen05_3xtf32_2cta_256x128x32_presplitB", 2);
 }
 
 }  // namespace tc
 
 // op(B) is pre-split into the handle's arena when both halves fit in PRESPLIT_LIMIT bytes and B is re-read
 // by at least two M-tiles; B then needs no alignment at all (the pre-pass reads any ldb).
-constexpr size_t PRESPLIT_LIMIT = size_t(512) << 20;
+constexpr size_t PRESPLIT_LIMIT = size_t(4) << 30;  // 16384^2 floats of B -> 2 GB of arena; beyond that B is split per tile in shared memory
 
 static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k) {
   if (opt(h, "sgemm.presplit", 1) == 0) return false;
@@ -869,7 +910,7 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
   const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   // CTA pairs (cta_group::2) whenever there are at least two M-tiles to pair and op(B) is pre-split: each CTA then loads
   // only its half of the tile's B columns (box {32, 64})
-  const bool use_pair = !tri && presplit && p.tiles_m >= 2 && opt(h, "sgemm.pair", 1) != 0;
+  const bool use_pair = presplit && p.tiles_m >= 2 && opt(h, "sgemm.pair", 1) != 0;
   const int bn_box = use_pair ? BN / 2 : BN;
   // A is only ever read by the split warps (it reaches the MMA through TMEM): an M-contiguous tile needs no swizzle
   bool ok = ta ? make_map(&ma, A, k, m, lda, BK, BM, kmaj) : make_map(&ma, A, m, k, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE);

@@ -85,7 +85,18 @@ def test_ssyrk_runs_on_tcgen05(oracle, handle):
     for lower in (0, 1):
         for trans in (0, 1):
             name = _syrk_case(oracle, handle, np.float32, lower, trans, 384, 512, 1.0, 0.0, 650)
-            assert name.startswith("ssyrk_tcgen05_3xtf32"), name
+            assert name.startswith("ssyrk_tcgen05_3xtf32_2cta"), name   # CTA pairs walk the triangle pair row by pair row
+            # even and odd numbers of 128-row tiles, several pair rows, ragged last tile, beta != 0, padded C; and the
+            # single-CTA kernel on the same problem
+            for n, k, beta in ((1024, 96, 0.0), (1000, 130, -0.5), (641, 64, 1.0)):
+                name = _syrk_case(oracle, handle, np.float32, lower, trans, n, k, 1.25, beta, 670 + n, ldc_pad=3)
+                assert name.startswith("ssyrk_tcgen05_3xtf32_2cta"), name
+            handle.set_option("sgemm.pair", 0)
+            try:
+                name = _syrk_case(oracle, handle, np.float32, lower, trans, 1000, 130, 1.25, -0.5, 1670, ldc_pad=3)
+            finally:
+                handle.set_option("sgemm.pair", 1)
+            assert name.startswith("ssyrk_tcgen05_3xtf32_128x128"), name
             name = _syrk_case(oracle, handle, np.float32, lower, trans, 200, 96, 1.0, 0.5, 660, lda_pad=1)
             assert name.startswith("ssyrk_tcgen05_3xtf32") and name.endswith("_padA"), name  # odd ld: aligned copy of A first
             handle.set_option("sgemm.pad_a", 0)

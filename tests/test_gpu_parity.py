@@ -599,6 +599,39 @@ def test_sgemm_tcgen05_pads_an_op_a_tma_cannot_address(oracle, handle, ta, tb):
     assert handle.last_kernel().startswith("sgemm_simt"), handle.last_kernel()
 
 
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_sgemm_tcgen05_propagates_nan_from_either_operand(handle, ta, tb):
+    """op(A) is split in registers with integer rounding (big) and an unrounded difference (small); a NaN of any payload —
+    the canonical 0x7fffffff and 0xffffffff overflow the rounding add — must still reach every entry of its row of C, a NaN
+    in op(B) every entry of its column, and nothing else."""
+    m, n, k = 300, 200, 160
+    for pattern in (0x7FC00000, 0x7FFFFFFF, 0xFFFFFFFF, 0x7F800001):
+        for pair in (1, 0):
+            handle.set_option("sgemm.variant", 2)
+            handle.set_option("sgemm.pair", pair)
+            try:
+                ar, ac = (k, m) if ta else (m, k)
+                br, bc = (n, k) if tb else (k, n)
+                g = torch.Generator(device="cuda").manual_seed(pattern & 0xFFFF)
+                A = torch.rand(ar * ac, dtype=torch.float32, device="cuda", generator=g) - 0.5
+                B = torch.rand(br * bc, dtype=torch.float32, device="cuda", generator=g) - 0.5
+                i0, l0, j0, l1 = 137, 45, 77, 101
+                nan = torch.tensor([pattern - (1 << 32) if pattern >= (1 << 31) else pattern], dtype=torch.int32, device="cuda").view(torch.float32)
+                A.view(ac, ar)[(i0, l0) if ta else (l0, i0)] = nan[0]       # op(A)[i0, l0]
+                B.view(bc, br)[(l1, j0) if tb else (j0, l1)] = nan[0]       # op(B)[l1, j0]
+                Cm = torch.zeros(m * n, dtype=torch.float32, device="cuda")
+                handle.gemm(False, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+                torch.cuda.synchronize()
+                got = torch.isnan(Cm.view(n, m).t())                          # (m, n)
+                want = torch.zeros_like(got)
+                want[i0, :] = True
+                want[:, j0] = True
+                assert torch.equal(got, want), (hex(pattern), pair, handle.last_kernel(), int(got.sum()), int(want.sum()))
+            finally:
+                handle.set_option("sgemm.variant", 0)
+                handle.set_option("sgemm.pair", 1)
+
+
 def test_sgemm_tcgen05_rejects_what_tma_cannot_address(handle):
     handle.set_option("sgemm.variant", 2)
     handle.set_option("sgemm.pad_a", 0)

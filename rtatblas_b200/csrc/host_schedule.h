@@ -68,26 +68,39 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
   }
   const int kp = panels > 1 ? ((k + panels - 1) / panels + 15) / 16 * 16 : k;
   int npanels = 0;
-  // Head of the single-GPU schedule when the leading blocks' product is clearly longer than the panel's upload (growth
-  // = t_product / t_upload - 1 per k-row >= 0.25; config 5: 0.37): the first panel is what the GPU waits for, so it starts at
-  // 256 k and each panel may exceed the first by `growth` times everything uploaded before it — the largest step that never
-  // lets the product of panel p - 1 end before panel p has landed — until the regular width kp is reached (config 5: 1.5 ms
-  // instead of 12 ms before the first product starts, for seven more beta = 1 passes).  Balanced problems (config 2: lead is
-  // chosen so that product and upload take equally long, growth ~ 0) keep the halved first panel below.
+  // Head of the single-GPU schedule: the first panel is what the GPU waits for, so it starts at 256 k and each panel may
+  // exceed the first by `growth` times everything uploaded before it — growth = t_product / t_upload - 1 per k-row, the
+  // largest step that never lets the product of panel p - 1 end before panel p has landed (config 5: 0.37, 1.5 ms instead
+  // of 12 ms before the first product starts).  A balanced problem — `lead` above makes product and upload take equally
+  // long, growth ~ 0.07 on config 2 — has no slack to grow into and its steady state stalls on every upload hiccup, so it
+  // takes ONE MORE leading block when that buys a growth of 0.15 or more (config 2: 5 leading blocks, growth 0.24; end to
+  // end 33.03 -> 32.3 ms, probe/perf_host2.py: the halved-first-panel schedule left the math waiting 0.85 ms for panel 2
+  // and ran every panel product against an upload just as long).  Panels keep growing past the regular width kp (deeper
+  // products, fewer beta = 1 passes over the leading blocks' C) up to 4 kp.
   double growth = 0.0;
-  if (!multi && panels > 1 && lead > 0 && opt_panels == 0) {
+  if (!multi && panels > 1 && lead > 0 && opt_panels <= 0) {
     const double rate = elem == 8 ? 33e12 : 150e12;
-    const double lead_cols = double(nb) * lead;
-    const double t_up = (double(bytes_a) / k * a_share + double(elem) * lead_cols) / pcie_rate, t_mm = 2.0 * m * lead_cols / rate;
-    growth = t_mm / t_up - 1.0;
+    auto growth_of = [&](int ld) {
+      const double lead_cols = double(nb) * ld;
+      const double t_up = (double(bytes_a) / k * a_share + double(elem) * lead_cols) / pcie_rate, t_mm = 2.0 * m * lead_cols / rate;
+      return t_mm / t_up - 1.0;
+    };
+    growth = growth_of(lead);
+    // the tapered tail keeps at least two full blocks' worth of columns for phase 2 (their products hide the copies back)
+    if (growth < 0.15 && opt_lead == 0 && (lead + 3) * nb <= n && growth_of(lead + 1) >= 0.15) growth = growth_of(++lead);
+    // experiments: host.panels = -g forces the growing head with a growth of at least g per cent
+    if (opt_panels < 0 && growth < -0.01 * opt_panels) growth = -0.01 * opt_panels;
   }
-  if (growth >= 0.25 && kp >= 1024) {
+  if ((growth >= 0.15 || opt_panels < 0) && kp >= 1024) {
     if (growth > 1.0) growth = 1.0;
+    const int wmax = 4 * kp;
     int done = 0;
     while (done < k && npanels < HostSchedule::PANEL_CAP - 1) {
       int w = npanels == 0 ? 256 : int(256 + growth * done) / 16 * 16;
-      if (w > kp) w = kp;
+      if (w > wmax) w = wmax;
       if (done + w > k || npanels == HostSchedule::PANEL_CAP - 2) w = k - done;
+      // a sliver left over would be one more pass over C for nothing: the last panel takes it
+      if (k - done - w < 256) w = k - done;
       sc.k0s[npanels] = done;
       sc.kcs[npanels++] = w;
       done += w;

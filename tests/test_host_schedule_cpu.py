@@ -53,20 +53,26 @@ def test_small_or_shallow_problems_take_the_plain_column_block_pipeline():
 
 
 def test_baseline_config_schedules_match_the_design_notes():
-    # config 2 (8192^3, op TN): 8 K-panels of 1024 with the first one halved, 9 column blocks (the last of 8 halved), 4 leading
+    # config 2 (8192^3, op TN): four leading blocks would balance product and upload exactly (growth 0.07), so it takes a
+    # fifth (growth 0.24) and a head growing from 256 k; 10 column blocks (the last of 8 tapered down to 256 columns)
     sc = rt.host_schedule(8, 1, 8192, 8192, 8192, 8192)
-    assert sc["panels"] == [(0, 512), (512, 512)] + [(1024 * i, 1024) for i in range(1, 8)]
+    widths = [kc for _, kc in sc["panels"]]
+    assert sc["lead"] == 5 and widths[0] == 256 and sum(widths) == 8192 and len(widths) <= 13
+    assert all(w <= 256 + 0.25 * sum(widths[:i]) + 16 for i, w in enumerate(widths[:-1]))
+    assert all(b >= a for a, b in zip(widths[:-2], widths[1:-1])) and widths[-1] >= 256
     assert [c for _, c in sc["blocks"]] == [1024] * 7 + [512, 256, 256]   # tapered tail: only 256 columns' copy back is exposed
-    assert sc["lead"] == 4
+    # the override keeps round 2's first schedule reachable: 8 panels of 1024 with the first one halved, 4 leading blocks
+    sc = rt.host_schedule(8, 1, 8192, 8192, 8192, 8192, panels=8, lead=4)
+    assert sc["panels"] == [(0, 512), (512, 512)] + [(1024 * i, 1024) for i in range(1, 8)] and sc["lead"] == 4
     # config 3 (4097 x 3001 x 2049, op NT): every block is a leading one (the transfer of A dominates)
     sc = rt.host_schedule(8, 0, 4097, 3001, 2049, 4097)
     assert sc["lead"] == len(sc["blocks"]) and len(sc["panels"]) == 3
     # config 5 on one GPU: one leading block whose product is 1.4x its panel's upload -> a head growing from 256 k by 0.37 of
-    # what is already up to the regular 4096, and a tail tapered from 4096 columns down to 256
+    # what is already up (no longer capped at the regular 4096), and a tail tapered from 4096 columns down to 256
     sc = rt.host_schedule(8, 0, 32768, 32768, 32768, 32768)
     widths = [kc for _, kc in sc["panels"]]
-    assert sc["lead"] == 1 and widths[0] == 256 and widths[-2] == 4096 and max(widths) == 4096
-    assert all(b >= a for a, b in zip(widths[:-1], widths[1:-1] + [4096])) and len(widths) <= 20
+    assert sc["lead"] == 1 and widths[0] == 256 and max(widths) <= 4 * 4096 and sum(widths) == 32768
+    assert all(b >= a for a, b in zip(widths[:-2], widths[1:-1])) and len(widths) <= 20
     assert all(w <= 256 + 0.38 * sum(widths[:i]) + 16 for i, w in enumerate(widths[:-1]))
     assert [c for _, c in sc["blocks"]][-5:] == [2048, 1024, 512, 256, 256]
     # config 5 per rank (m = k = 32768, n = 32768 / world): the multi-GPU caller's margin on the leading blocks

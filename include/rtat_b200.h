@@ -133,7 +133,10 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *   explicitly (0 = automatic).  Used by the tests to force every code path and by the planner's
  *   fused/explicit plan dimension.  The other keys are switches for A/B measurements and tests; unknown
  *   keys are stored and ignored.  (Defaults in brackets.)
- *     dgemm.tile [0]            128 / 64: force the tile configuration of the persistent DGEMM
+ *     dgemm.tile [0]            128 / 64 / 192 (= 128x64 tiles): force the tile configuration of the persistent DGEMM
+ *     dgemm.mid [1]             0: the automatic choice never takes 128x64 tiles
+ *     dgemm.skinny [1]          0: thin strips and GEMV-shaped calls (at most 4 rows / columns of C) stay on the tile kernels
+ *     dgemm.ktail [1]           0: the last k-tile of a k that is not a multiple of 16 runs all four DMMA steps
  *     dgemm.streamk [1]         0: data-parallel schedule only
  *     dgemm.tma3d [1]           0: eight 2-D TMA boxes per M/N-contiguous operand stage instead of one 3-D box
  *     dgemm.peel [1]            0: keep remainders of 1..16 rows / columns in the 128x128 launch instead of a second

@@ -1,5 +1,7 @@
 // C ABI entry points (include/rtat_b200.h): handle management, argument validation, dispatch.
 // Replaces the cuBLAS side of the reference's rtat::gpu:: alias table (src/gpu-api/gpu-api.h:87-113).
+#include <string>
+#include <cstdlib>
 #include "common.cuh"
 #include "host_pipeline.cuh"
 #include <cstring>
@@ -85,6 +87,20 @@ int rtat_b200_create(rtat_b200_handle_t *handle) {
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
   h->stream = nullptr;  // legacy default stream until set_stream, as with cuBLAS
+  // RTAT_B200_OPTIONS="key=value,key=value": option overrides for every handle of the process, so that experiments reach
+  // the kernels through any caller (the C++ planner, run_tests, the reference's own host code over this ABI)
+  if (const char *env = getenv("RTAT_B200_OPTIONS")) {
+    std::string all(env);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string kv = all.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos && eq > 0) h->options[kv.substr(0, eq)] = atoi(kv.c_str() + eq + 1);
+      pos = end + 1;
+    }
+  }
   *handle = h;
   return RTAT_B200_STATUS_SUCCESS;
 }

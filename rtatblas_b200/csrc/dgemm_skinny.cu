@@ -1,0 +1,231 @@
+// Skinny DGEMM: the thin remainder strips the persistent kernel peels off (dgemm_ws.cu: m % 128 or n % tile in 1..16).
+//
+//   Y (r x N) = alpha * S (r x K) * X (K x N) + beta * Y,   r <= 4
+//
+// with generic element strides, so that one kernel serves the row strip of C (S = the last rows of op(A), X = op(B),
+// Y = those rows of C) and, transposed, the column strip (S = the last columns of op(B), X = op(A)^T, Y = those columns
+// of C read as rows).  Part of the replacement of cublasDgemm behind MatrixMult (reference src/matrix_ops/matrixop.h:15-46).
+//
+// Such a strip is a handful of GEMVs: the work is reading X once (config 3: 1 x 3001 x 2049, 49 MB), which the tile
+// kernel cannot do cheaply — a 64x64 tile per 64 columns of X, each cut across six CTAs by stream-K with a 32 KB partial
+// tile parked and fetched per cut, 30-35 us for one row of C.  Here every thread owns output columns, S lives in shared
+// memory, X streams through registers, FP64 FMA pipe (r FMAs per element of X).  Measured against the tile kernel on
+// 1..16 x 3001 x 2049 and 8192-wide strips (probe/perf_skinny2.py): r = 1 1.3-2.4x faster, r = 4 1.0-1.4x, r = 8 and 16
+// slower (the FMA pipe delivers ~6 TFLOP/s here), so strips wider than 4 stay on the tile kernel.
+//
+//   X contiguous along N (xs_j == 1): thread j of a CTA owns column j; a warp reads 256 contiguous bytes of one k-row.
+//   X contiguous along K (xs_k == 1): a warp owns JW columns, lanes stride over k (256 contiguous bytes of one column
+//                                     per load) and the r x JW sums are folded with shuffles.
+//
+// K is cut into chunks, one CTA per (column block, chunk), so that a strip a few thousand columns wide still fills the
+// machine; partial sums go to the handle's arena and a second small kernel adds them IN CHUNK ORDER (deterministic, like
+// the stream-K fix-up) and applies alpha / beta.  One chunk: the first kernel finishes Y itself.
+#include "common.cuh"
+
+namespace rtat_b200 {
+
+int ensure_arena(rtat_b200_context *h, size_t bytes);
+
+namespace skinny {
+
+struct Params {
+  int r, N, K;
+  const double *S;
+  long long ss_i, ss_k;
+  const double *X;
+  long long xs_k, xs_j;
+  double *Y;
+  long long ys_i, ys_j;
+  double alpha, beta;
+  int kc, nchunks, jblocks;
+  double *partial;  // [nchunks][R][N] when nchunks > 1
+};
+
+constexpr int THREADS = 128;
+constexpr int SKINNY_MAX_ROWS = 4;
+
+// S chunk -> shared memory, zero beyond the strip's r rows and the chunk's valid k.  The faster index follows S's
+// contiguous direction.
+template <int R, int KC, bool K_MAJOR /* sm[kk][i] (true) or sm[i][kk] */>
+__device__ __forceinline__ void load_s(double *sm, const Params &p, int k0, int kc) {
+  for (int idx = threadIdx.x; idx < R * KC; idx += THREADS) {
+    int i, kk;
+    if (p.ss_k == 1) { kk = idx % KC; i = idx / KC; } else { i = idx % R; kk = idx / R; }
+    double v = 0.0;
+    if (i < p.r && kk < kc) v = p.S[i * p.ss_i + (long long)(k0 + kk) * p.ss_k];
+    sm[K_MAJOR ? kk * R + i : i * KC + kk] = v;
+  }
+}
+
+__device__ __forceinline__ void finish(const Params &p, int i, int j, double sum) {
+  double *y = p.Y + i * p.ys_i + j * p.ys_j;
+  double v = p.alpha * sum;
+  if (p.beta != 0.0) v += p.beta * *y;
+  *y = v;
+}
+
+// ---- X contiguous along N ---------------------------------------------------------------------------------------
+template <int R, int KC>
+__global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
+  __shared__ __align__(16) double sm[KC * R];
+  const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
+  const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
+  const int j = jb * THREADS + threadIdx.x;
+  const bool active = j < p.N;
+  double acc[R];
+#pragma unroll
+  for (int i = 0; i < R; i++) acc[i] = 0.0;
+  for (int k0 = k_begin; k0 < k_end; k0 += KC) {
+    const int kc = min(KC, k_end - k0);
+    __syncthreads();  // the previous unit's S tile has been read
+    load_s<R, KC, true>(sm, p, k0, kc);
+    __syncthreads();
+    if (!active) continue;
+    const double *xp = p.X + (long long)k0 * p.xs_k + j;
+    constexpr int U = R <= 2 ? 16 : 8;  // loads in flight per thread: a GEMV lives on memory-level parallelism
+    for (int kk = 0; kk < kc; kk += U) {
+      double x[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) x[u] = (kk + u < kc) ? __ldg(xp + (long long)(kk + u) * p.xs_k) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int i = 0; i < R; i++) acc[i] = fma(sm[(kk + u) * R + i], x[u], acc[i]);  // rows of sm beyond kc are zero
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    if (i >= p.r) break;
+    if (p.nchunks == 1) finish(p, i, j, acc[i]);
+    else __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[i]);
+  }
+}
+
+// ---- X contiguous along K ---------------------------------------------------------------------------------------
+template <int R, int KC, int JW>
+__global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
+  __shared__ __align__(16) double sm[R * KC];
+  const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
+  const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int j0 = (jb * (THREADS / 32) + warp) * JW;
+  const bool active = j0 < p.N;
+  double acc[JW][R];
+#pragma unroll
+  for (int jj = 0; jj < JW; jj++)
+#pragma unroll
+    for (int i = 0; i < R; i++) acc[jj][i] = 0.0;
+  const double *xp[JW];
+#pragma unroll
+  for (int jj = 0; jj < JW; jj++) xp[jj] = p.X + (long long)min(j0 + jj, p.N - 1) * p.xs_j;  // clamped: never stored
+  for (int k0 = k_begin; k0 < k_end; k0 += KC) {
+    const int kc = min(KC, k_end - k0);
+    __syncthreads();
+    load_s<R, KC, false>(sm, p, k0, kc);
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll
+    for (int t = 0; t < KC / 32; t++) {
+      const int kk = lane + 32 * t;
+      double x[JW];
+#pragma unroll
+      for (int jj = 0; jj < JW; jj++) x[jj] = kk < kc ? __ldg(xp[jj] + k0 + kk) : 0.0;
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        const double sv = sm[i * KC + kk];
+#pragma unroll
+        for (int jj = 0; jj < JW; jj++) acc[jj][i] = fma(sv, x[jj], acc[jj][i]);
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int jj = 0; jj < JW; jj++)
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      double v = acc[jj][i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[jj][i] = v;
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int jj = 0; jj < JW; jj++) {
+      const int j = j0 + jj;
+      if (j >= p.N) break;
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        if (i >= p.r) break;
+        if (p.nchunks == 1) finish(p, i, j, acc[jj][i]);
+        else __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[jj][i]);
+      }
+    }
+  }
+}
+
+// partial sums -> Y, chunks added in order
+__global__ void __launch_bounds__(THREADS) skinny_reduce_kernel(const Params p, int R) {
+  const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
+  if (idx >= (long long)p.r * p.N) return;
+  const int i = int(idx / p.N), j = int(idx % p.N);
+  double sum = 0.0;
+  for (int c = 0; c < p.nchunks; c++) sum += __ldcg(p.partial + ((size_t)c * R + i) * p.N + j);
+  finish(p, i, j, sum);
+}
+
+template <int R>
+static int run(rtat_b200_context *h, Params p) {
+  const bool xj = p.xs_j == 1;
+  // k per shared-memory S tile (R x KC doubles): short tiles give the N-contiguous GEMVs more CTAs (1 x 8192 x 2048:
+  // 42 -> 31 us); the K-contiguous kernel folds its sums with shuffles once per chunk and wants chunks of 512 k or more
+  // (256: 37 -> 49 us)
+  constexpr int KCJ = R <= 2 ? 64 : 128, KCK = 128;
+  constexpr int JW = 4;                         // columns per warp of the K-contiguous kernel
+  const int KC = xj ? KCJ : KCK;
+  const int cols_per_cta = xj ? THREADS : (THREADS / 32) * JW;
+  p.jblocks = (p.N + cols_per_cta - 1) / cols_per_cta;
+  // chunks of whole S tiles: enough CTAs for 6-8 per SM
+  const int units = (p.K + KC - 1) / KC;
+  int nchunks = ((xj ? 8 : 6) * h->sm_count + p.jblocks - 1) / p.jblocks;
+  if (nchunks > units) nchunks = units;
+  if (!xj && nchunks > (units + 3) / 4) nchunks = (units + 3) / 4;
+  if (nchunks < 1) nchunks = 1;
+  p.kc = ((units + nchunks - 1) / nchunks) * KC;
+  p.nchunks = (p.K + p.kc - 1) / p.kc;
+  if (p.nchunks > 1) {
+    const size_t bytes = sizeof(double) * (size_t)p.nchunks * R * p.N;
+    if (bytes > (size_t(256) << 20)) return RTAT_B200_STATUS_NOT_SUPPORTED;
+    if (int st = ensure_arena(h, bytes)) return st;
+    p.partial = static_cast<double *>(h->arena);
+  }
+  const long long grid = (long long)p.jblocks * p.nchunks;
+  if (grid > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  if (xj) skinny_xj_kernel<R, KCJ><<<(unsigned)grid, THREADS, 0, h->stream>>>(p);
+  else skinny_xk_kernel<R, KCK, JW><<<(unsigned)grid, THREADS, 0, h->stream>>>(p);
+  int st = check_launch(h, xj ? "dgemm_skinny_fma_xn" : "dgemm_skinny_fma_xk");
+  if (st || p.nchunks == 1) return st;
+  const long long outs = (long long)p.r * p.N;
+  skinny_reduce_kernel<<<(unsigned)((outs + THREADS - 1) / THREADS), THREADS, 0, h->stream>>>(p, R);
+  return check_launch(h, xj ? "dgemm_skinny_fma_xn+reduce" : "dgemm_skinny_fma_xk+reduce");
+}
+
+}  // namespace skinny
+
+// Y (r x N) = alpha S X + beta Y with element strides; NOT_SUPPORTED when the strip is not skinny or X has no unit stride.
+int dgemm_skinny(rtat_b200_context *h, int r, int N, int K, double alpha, const double *S, long long ss_i, long long ss_k, const double *X,
+                 long long xs_k, long long xs_j, double beta, double *Y, long long ys_i, long long ys_j) {
+  // Wider strips are FMA-bound here (r = 8: 6 TFLOP/s, slower than the tile kernel's padded DMMAs): measured break-even r = 4
+  if (r < 1 || r > skinny::SKINNY_MAX_ROWS || N < 1 || K < 1 || (xs_k != 1 && xs_j != 1)) return RTAT_B200_STATUS_NOT_SUPPORTED;
+  skinny::Params p{};
+  p.r = r; p.N = N; p.K = K;
+  p.S = S; p.ss_i = ss_i; p.ss_k = ss_k;
+  p.X = X; p.xs_k = xs_k; p.xs_j = xs_j;
+  p.Y = Y; p.ys_i = ys_i; p.ys_j = ys_j;
+  p.alpha = alpha; p.beta = beta;
+  if (r == 1) return skinny::run<1>(h, p);
+  if (r == 2) return skinny::run<2>(h, p);
+  return skinny::run<4>(h, p);
+}
+
+}  // namespace rtat_b200

@@ -49,12 +49,17 @@ struct TileCfg {
   static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // consumers of a ragged tile skip single DMMA blocks (64x64 tiles) or only whole warps (128x128: at the register cap)
   static constexpr bool FINE_EDGES = BM_ == 64;
-  // 128x128 tiles: the consumers need more registers than an even split of the file gives them (setmaxnreg, see the
-  // kernel); 64x64 tiles hold 64 accumulator registers and do not (measured with the split: 1-3 % slower)
+  // 64x32 warp tiles (128 accumulator registers): the consumers need more registers than an even split of the file gives
+  // them (setmaxnreg, see the kernel); 64x64 tiles hold 64 accumulator registers and do not (measured with the split: 1-3 %
+  // slower)
   static constexpr bool SPLIT_REGS = BM_ == 128;
 };
 using Cfg128 = TileCfg<128, 128, 64, 32, 6, 1>;
 using Cfg64 = TileCfg<64, 64, 32, 32, 6, 2>;
+// 128x64 tiles, four 64x32 consumer warps, two CTAs per SM (4 stages of 24 KB each): the warp tile — and with it the
+// fragment loads and ring hand-offs per DMMA — of the 128x128 configuration at half the tile area: twice the tiles to
+// balance, half the stream-K slot, N quantised in 64s.
+using Cfg128x64 = TileCfg<128, 64, 64, 32, 4, 2>;
 
 struct Params {
   int m, n, k;
@@ -91,6 +96,7 @@ struct Params {
   // rows of op(A) / columns of op(B) the operand's 3-D map covers (see tma_load_3d; 0 = no 3-D map): a tile wholly below
   // the limit is ONE box per stage, the ragged last tile row / column takes the 2-D boxes
   int a_3d, b_3d;
+  int tail_steps;  // DMMA steps of the last k-tile that see a valid k (1..4; 4 when k is a multiple of 16): see mma_ktile
   int prefetch_c;  // beta != 0: consumers prefetch their part of the C tile into L2 when the tile starts (option dgemm.prefetch_c)
 };
 
@@ -286,6 +292,33 @@ __device__ __forceinline__ void load_half(double (&f)[2][NBLK], const FragAddr<K
   }
 }
 
+// DMMAs of one k-tile on one warp tile.  ALL: every block (interior tile); otherwise the first mi_act x ni_act blocks.
+// FULL: all four DMMA steps; otherwise only the first `steps` of them — the last k-tile of a K that is not a multiple of 16
+// holds k_rem valid k's and step ks multiplies k = 2q + (ks & 1) + 8 (ks >> 1) (kmap), so steps whose smallest k is beyond
+// k_rem would only add the producers' zero fill (K = 2049, config 3: three of the 129th k-tile's four steps).
+template <bool KCA, bool KCB, int MI, int NI, bool ALL, bool FULL>
+__device__ __forceinline__ void mma_ktile(double (&acc)[MI][NI][2], const FragAddr<KCA> &fa_addr, const FragAddr<KCB> &fb_addr, uint32_t sbase,
+                                          int mi_act, int ni_act, int steps) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    if (!FULL && 2 * h >= steps) break;
+    double fa[2][MI], fb[2][NI];
+    load_half<KCA, MI, ALL>(fa, fa_addr, sbase, h, mi_act);
+    load_half<KCB, NI, ALL>(fb, fb_addr, sbase, h, ni_act);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      if (!FULL && 2 * h + e >= steps) break;
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+        if (ALL || i < mi_act) {
+#pragma unroll
+          for (int j = 0; j < NI; j++)
+            if (ALL || j < ni_act) dmma(acc[i][j], fa[e][i], fb[e][j]);
+        }
+    }
+  }
+}
+
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
 }
@@ -406,7 +439,8 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int PRODUCER_REGS = USE_TMA ? 40 : 56;
   constexpr int LAUNCH_REGS = 65536 / ((CONSUMER_WARPS + CPASYNC_PRODUCER_WARPS) * 32 * Cfg::CTAS_PER_SM) / 8 * 8;
   constexpr int CONSUMER_REGS = (LAUNCH_REGS + (LAUNCH_REGS - PRODUCER_REGS) * CPASYNC_PRODUCER_WARPS / CONSUMER_WARPS) / 8 * 8;
-  static_assert(!Cfg::SPLIT_REGS || BM != 128 || CONSUMER_REGS == 232 || CONSUMER_REGS == 224, "128x128 split as measured");
+  static_assert(!Cfg::SPLIT_REGS || BN != 128 || CONSUMER_REGS == 232 || CONSUMER_REGS == 224, "128x128 split as measured");
+  static_assert(!Cfg::SPLIT_REGS || BN != 64 || CONSUMER_REGS == 216 || CONSUMER_REGS == 200, "128x64 split: half a register file per CTA");
   if (warp >= CONSUMER_WARPS) {
     if (Cfg::SPLIT_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PRODUCER_REGS));
     // ======================= producer =======================
@@ -516,51 +550,31 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int mi_act = KCA ? (rv + 7) / 8 : 2 * ((rv + 15) / 16), ni_act = KCB ? (cv + 7) / 8 : 2 * ((cv + 15) / 16);
     const bool whole = mi_act == MI && ni_act == NI;
     static_assert(KS == 4, "two halves of two DMMA steps per k-tile");
+    // the last k-tile of the tile runs apart when only some of its DMMA steps see a valid k (mma_ktile)
+    const int ke_main = (seg.ke == p.kt && p.tail_steps < KS) ? seg.ke - 1 : seg.ke;
     if (whole || !Cfg::FINE_EDGES) {
-      // 128x128 tiles (no registers to spare for a second loop body) skip at warp granularity only
+      // 64-row warp tiles (no registers to spare for a second loop body) skip at warp granularity only
       const bool active = whole || (mi_act > 0 && ni_act > 0);
-      for (int kt = seg.kb; kt < seg.ke; kt++) {
+      for (int kt = seg.kb; kt < ke_main; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
-        if (active) {
-          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            double fa[2][MI], fb[2][NI];
-            load_half<KCA, MI, true>(fa, fa_addr, sbase, h, MI);
-            load_half<KCB, NI, true>(fb, fb_addr, sbase, h, NI);
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-#pragma unroll
-              for (int i = 0; i < MI; i++)
-#pragma unroll
-                for (int j = 0; j < NI; j++) dmma(acc[i][j], fa[e][i], fb[e][j]);
-          }
-        }
+        if (active) mma_ktile<KCA, KCB, MI, NI, true, true>(acc, fa_addr, fb_addr, smem_base + stage * STAGE_BYTES, MI, NI, KS);
+        release_stage(bar_base + 8 * (STAGES + stage), lane);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (ke_main < seg.ke) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (active) mma_ktile<KCA, KCB, MI, NI, true, false>(acc, fa_addr, fb_addr, smem_base + stage * STAGE_BYTES, MI, NI, p.tail_steps);
         release_stage(bar_base + 8 * (STAGES + stage), lane);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     } else {
       // ragged tile (or a warp with nothing to do): same ring protocol, only the blocks that touch C are multiplied
+      const bool active = mi_act > 0 && ni_act > 0;
       for (int kt = seg.kb; kt < seg.ke; kt++) {
         mbar_wait(bar_base + 8 * stage, phase);
-        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-        if (mi_act > 0 && ni_act > 0) {
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            double fa[2][MI], fb[2][NI];
-            load_half<KCA, MI, false>(fa, fa_addr, sbase, h, mi_act);
-            load_half<KCB, NI, false>(fb, fb_addr, sbase, h, ni_act);
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-#pragma unroll
-              for (int i = 0; i < MI; i++)
-                if (i < mi_act) {
-#pragma unroll
-                  for (int j = 0; j < NI; j++)
-                    if (j < ni_act) dmma(acc[i][j], fa[e][i], fb[e][j]);
-                }
-          }
-        }
+        if (active)
+          mma_ktile<KCA, KCB, MI, NI, false, false>(acc, fa_addr, fb_addr, smem_base + stage * STAGE_BYTES, mi_act, ni_act,
+                                                    kt < ke_main ? KS : p.tail_steps);
         release_stage(bar_base + 8 * (STAGES + stage), lane);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -715,6 +729,9 @@ static int launch(rtat_b200_context *h, const Params &p, int grid, const CUtenso
 
 }  // namespace ws
 
+int dgemm_skinny(rtat_b200_context *h, int r, int N, int K, double alpha, const double *S, long long ss_i, long long ss_k, const double *X,
+                 long long xs_k, long long xs_j, double beta, double *Y, long long ys_i, long long ys_j);
+
 bool dgemm_ws_tma_ok(const double *A, int lda, const double *B, int ldb) {
   auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 2 == 0; };
   return ok(A, lda) && ok(B, ldb);
@@ -798,6 +815,10 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
   if (tiles > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
   p.num_tiles = (int)tiles;
   p.kt = (k + BK - 1) / BK;
+  {
+    const int k_rem = k - (p.kt - 1) * BK;  // valid k's of the last k-tile, 1..16 (k >= 1 here)
+    p.tail_steps = (k_rem >= 10 || opt(h, "dgemm.ktail", 1) == 0) ? 4 : k_rem == 9 ? 3 : k_rem >= 2 ? 2 : 1;
+  }
   // ---- schedule: hybrid stream-K ---------------------------------------------------------------
   // grid: CTAS_PER_SM resident CTAs per SM, fewer when there are not even MIN_UNITS k-tiles of work per CTA.
   constexpr int MIN_UNITS = 4;
@@ -832,6 +853,8 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
     // reallocation (and its sync) later
     size_t arena = sizeof(double) * (size_t)Cfg128::SLOT_DOUBLES * h->sm_count * Cfg128::CTAS_PER_SM;
     size_t arena64 = sizeof(double) * (size_t)Cfg64::SLOT_DOUBLES * h->sm_count * Cfg64::CTAS_PER_SM;
+    const size_t arena12864 = sizeof(double) * (size_t)Cfg128x64::SLOT_DOUBLES * h->sm_count * Cfg128x64::CTAS_PER_SM;
+    if (arena64 < arena12864) arena64 = arena12864;
     int st = ensure_arena(h, arena > arena64 ? arena : arena64);
     if (st) return st;
     if (!h->sk_flags) {
@@ -878,67 +901,97 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
 #undef RTAT_WS
 }
 
-// tile_cfg: 0 = choose, 128 / 64 = forced.  tri: 0 = GEMM; 1 / 2 = SYRK on the lower / upper triangle (m == n, B is A
-// with the opposite op; only tiles touching the triangle are scheduled and the diagonal tiles are masked).
+// tile_cfg: 0 = choose, 128 / 64 = forced, 192 = 128x64 tiles.  tri: 0 = GEMM; 1 / 2 = SYRK on the lower / upper triangle
+// (m == n, B is A with the opposite op; only tiles touching the triangle are scheduled and the diagonal tiles are masked).
 int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
              const double *B, int ldb, double beta, double *C, int ldc, bool allow_tma, int tile_cfg, int tri) {
-  // Thin remainders are peeled off.  A 128x128 tile with only a few valid rows (or columns) costs a whole tile: its
+  // Thin remainders are peeled off.  A 128-row tile with only a few valid rows (or columns) costs a whole tile: its
   // consumers skip work at warp granularity only (they sit at the register cap), and with m % 128 <= PEEL_MAX the rows
-  // all belong to the same two of the eight warps' M-slice, i.e. to two busy warps on two of the four sub-partitions.  Config 3
+  // all belong to the same M-slice, i.e. to half the warps on two of the four sub-partitions.  Config 3
   // (m = 4097) spent 24 of its 792 tile times on ONE row of C.  Such a strip goes to a second, small launch on 64x64
-  // tiles (whose consumers skip single 8-row blocks) and the 128x128 launch sees a multiple of 128.
+  // tiles (whose consumers skip single 8-row blocks) and the main launch sees a multiple of its tile size.
   constexpr int PEEL_MAX = 16;
-  auto peelable = [&](int x) { return !tri && opt(h, "dgemm.peel", 1) != 0 && x % 128 > 0 && x % 128 <= PEEL_MAX && x >= 512; };
-  const int m_main = peelable(m) ? m - m % 128 : m, n_main = peelable(n) ? n - n % 128 : n;
-  const bool peel = m_main != m || n_main != n;
+  auto peeled = [&](int x, int b) { return (!tri && opt(h, "dgemm.peel", 1) != 0 && x % b > 0 && x % b <= PEEL_MAX && x >= 512) ? x - x % b : x; };
+  const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
   if (tile_cfg == 0) {
     // Estimated cost = padded tile area x waves.  128x128 tiles are the more efficient steady state
     // (98 % vs ~94 % of the DMMA pipe), 64x64 tiles waste less on ragged edges and keep stream-K fix-ups
     // four times smaller, which decides small problems.
     // ragged tiles are charged what their busiest sub-partition multiplies (tile_cost)
-    auto padded = [&](int bm, int mm, int nn) {
-      double tm = (mm + bm - 1) / bm, tn = (nn + bm - 1) / bm;
-      if (tri) return tm * (tm + 1) / 2 * bm * bm;
+    auto padded = [&](int bm, int bn, int mm, int nn) {
+      double tm = (mm + bm - 1) / bm, tn = (nn + bn - 1) / bn;
+      if (tri) return tm * (tm + 1) / 2 * bm * bn;
       const bool amn = !ta;
-      auto cost = [&](int rows, int cols) { return bm == 128 ? tile_cost<ws::Cfg128>(amn, rows, cols) : tile_cost<ws::Cfg64>(amn, rows, cols); };
-      double tmf = mm / bm, tnf = nn / bm, sixteenths = 16.0 * tmf * tnf;
-      if (nn % bm) sixteenths += tmf * cost(0, nn % bm);
+      auto cost = [&](int rows, int cols) {
+        return bn == 128 ? tile_cost<ws::Cfg128>(amn, rows, cols) : bm == 128 ? tile_cost<ws::Cfg128x64>(amn, rows, cols) : tile_cost<ws::Cfg64>(amn, rows, cols);
+      };
+      double tmf = mm / bm, tnf = nn / bn, sixteenths = 16.0 * tmf * tnf;
+      if (nn % bn) sixteenths += tmf * cost(0, nn % bn);
       if (mm % bm) sixteenths += tnf * cost(mm % bm, 0);
-      if (mm % bm && nn % bm) sixteenths += cost(mm % bm, nn % bm);
-      return sixteenths / 16.0 * bm * bm;
+      if (mm % bm && nn % bn) sixteenths += cost(mm % bm, nn % bn);
+      return sixteenths / 16.0 * bm * bn;
     };
     // measured steady-state efficiencies: TMA producers 0.985 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
-    const bool tma = allow_tma && dgemm_ws_tma_ok(A, lda, B, ldb);
     // the peeled strips ride along at the 64x64 rate plus ~5 us of fixed cost per launch (as C area: t x rate / 2k)
     const double launch_area = 5e-6 * 36e12 / (2.0 * (k > 0 ? k : 1));
-    double strips = peel ? (padded(64, m - m_main, n) + padded(64, m_main, n - n_main)) / (tma ? 0.96 : 0.85) +
-                               launch_area * ((m_main != m) + (n_main != n))
-                         : 0.0;
-    double t128 = padded(128, m_main, n_main) / (tma ? 0.985 : 0.92) + strips, t64 = padded(64, m, n) / (tma ? 0.96 : 0.85);
+    auto with_strips = [&](int bm, int bn, double eff) {
+      const int mm = peeled(m, bm), nn = peeled(n, bn);
+      double strips = (mm != m || nn != n) ? (padded(64, 64, m - mm, n) + padded(64, 64, mm, n - nn)) / (tma ? 0.96 : 0.85) + launch_area * ((mm != m) + (nn != n)) : 0.0;
+      return padded(bm, bn, mm, nn) / eff + strips;
+    };
+    double t128 = with_strips(128, 128, tma ? 0.985 : 0.92), t64 = padded(64, 64, m, n) / (tma ? 0.96 : 0.85);
     long long units128 = (long long)((m + 127) / 128) * ((n + 127) / 128) * ((k + 15) / 16) / (tri ? 2 : 1);
     bool small = units128 < (long long)h->sm_count * 64;  // under ~64 k-tiles per SM the fix-up chain is a visible tail
-    // 64x64 tiles pull twice the operand bytes through L2; when A and B fit in L2 that costs nothing and the two
+    // 128x64 tiles: the warp tile, and the steady state, of the 128x128 configuration (8192^3: 36.16 against 36.47 TF: one
+    // CTA's ring feeds half the DMMAs) with twice the tiles: from a dozen waves of 128x128 tiles down they balance better
+    // than they cost (4096^3 36.19 / 36.13, 3000^3 34.86 / 34.13, config 3's pad plan 1.450 / 1.477 ms; 64x64: 1.500).
+    // SYRK keeps the square tiles its triangle schedule assumes.
+    const double waves128 = (double)((m + 127) / 128) * ((n + 127) / 128) / h->sm_count;
+    double tmid = tri ? 1e300 : with_strips(128, 64, tma ? (waves128 >= 12.0 ? 0.977 : 0.987) : 0.91);
+    if (opt(h, "dgemm.mid", 1) == 0) tmid = 1e300;
+    // 64x64 tiles pull twice the operand bytes through L2; when A and B fit in L2 that costs nothing and the
     // estimates are closer than their error, so a peeled 128x128 schedule has to win by 3 % (config 3 inside the planner,
     // operands hot in L2 from the pad pass: 64x64 1.453 ms, 128x128 + strip 1.470; cold: 1.527 against 1.496)
     const bool l2_resident = 8.0 * ((double)m * k + (double)k * n) < 0.95 * (double)h->l2_bytes;
-    if (peel && l2_resident) t128 *= 1.03;
-    tile_cfg = (small || t64 < t128) ? 64 : 128;
+    if ((peeled(m, 128) != m || peeled(n, 128) != n) && l2_resident) t128 *= 1.03;
+    tile_cfg = (small || (t64 < t128 && t64 < tmid)) ? 64 : (tmid < t128 ? 192 : 128);
   }
   if (tile_cfg == 64)
     return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);
-  if (!peel) return run_cfg<ws::Cfg128>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
-  int st = run_cfg<ws::Cfg128>(h, ta, tb, m_main, n_main, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
+  const bool mid = tile_cfg == 192 && !tri;
+  const int m_main = peeled(m, 128), n_main = peeled(n, mid ? 64 : 128);
+  const bool peel = m_main != m || n_main != n;
+  auto main_launch = [&](int mm, int nn) {
+    return mid ? run_cfg<ws::Cfg128x64>(h, ta, tb, mm, nn, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x64x16", 0)
+               : run_cfg<ws::Cfg128>(h, ta, tb, mm, nn, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "128x128x16", tri);
+  };
+  if (!peel) return main_launch(m, n);
+  int st = main_launch(m_main, n_main);
   if (st) return st;
+  // The strips: at most 16 rows / columns of C each.  Up to 4 wide they are a handful of GEMVs and go to the skinny kernel
+  // (dgemm_skinny.cu), which reads the large operand once; wider ones stay on a 64x64-tile launch (one tile per 64
+  // columns, stream-K over every CTA: 27 us for config 3's single row against 16; option dgemm.skinny = 0: always).
+  const bool skinny = opt(h, "dgemm.skinny", 1) != 0;
   static thread_local char name[112];
-  snprintf(name, sizeof name, "%s+strips64", h->last_kernel);
+  const bool any_skinny = skinny && ((m_main != m && m - m_main <= 4) || (n_main != n && n - n_main <= 4));
+  snprintf(name, sizeof name, "%s+strips%s", h->last_kernel, any_skinny ? "_skinny" : "64");
   if (m_main != m) {  // rows [m_main, m), all columns
     const double *As = ta ? A + (size_t)m_main * lda : A + m_main;
-    st = run_cfg<ws::Cfg64>(h, ta, tb, m - m_main, n, k, alpha, As, lda, B, ldb, beta, C + m_main, ldc, allow_tma, "64x64x16", 0);
+    st = RTAT_B200_STATUS_NOT_SUPPORTED;
+    if (skinny)  // S = op(A) rows, X = op(B) (k x n), Y = rows of C
+      st = dgemm_skinny(h, m - m_main, n, k, alpha, As, ta ? lda : 1, ta ? 1 : lda, B, tb ? ldb : 1, tb ? 1 : ldb, beta, C + m_main, 1, ldc);
+    if (st == RTAT_B200_STATUS_NOT_SUPPORTED)
+      st = run_cfg<ws::Cfg64>(h, ta, tb, m - m_main, n, k, alpha, As, lda, B, ldb, beta, C + m_main, ldc, allow_tma, "64x64x16", 0);
     if (st) return st;
   }
   if (n_main != n) {  // columns [n_main, n) of the rows the main launch covered
     const double *Bs = tb ? B + n_main : B + (size_t)n_main * ldb;
-    st = run_cfg<ws::Cfg64>(h, ta, tb, m_main, n - n_main, k, alpha, A, lda, Bs, ldb, beta, C + (size_t)n_main * ldc, ldc, allow_tma, "64x64x16", 0);
+    st = RTAT_B200_STATUS_NOT_SUPPORTED;
+    if (skinny)  // transposed: S = op(B)^T rows (the strip's columns), X = op(A)^T (k x m_main), Y = columns of C read as rows
+      st = dgemm_skinny(h, n - n_main, m_main, k, alpha, Bs, tb ? 1 : ldb, tb ? ldb : 1, A, ta ? 1 : lda, ta ? lda : 1, beta,
+                        C + (size_t)n_main * ldc, ldc, 1);
+    if (st == RTAT_B200_STATUS_NOT_SUPPORTED)
+      st = run_cfg<ws::Cfg64>(h, ta, tb, m_main, n - n_main, k, alpha, A, lda, Bs, ldb, beta, C + (size_t)n_main * ldc, ldc, allow_tma, "64x64x16", 0);
     if (st) return st;
   }
   h->last_kernel = name;

@@ -67,7 +67,7 @@ def test_dgemm_reference_test_shapes(oracle, handle, ta, tb, variant):
 
 
 @pytest.mark.parametrize("ta,tb", OPS)
-@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (3, 64)])
+@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (3, 64), (3, 192)])
 def test_dgemm_tile_boundaries_and_alignment(oracle, handle, ta, tb, variant, tile):
     handle.set_option("dgemm.variant", variant)
     handle.set_option("dgemm.tile", tile)
@@ -126,7 +126,7 @@ def test_sgemm_reference_test_shapes(oracle, handle, ta, tb):
         _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.5, -0.5, 500 + m, lda_pad=1, ldb_pad=2, ldc_pad=3)
 
 
-@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (4, 128), (3, 64), (4, 64)])
+@pytest.mark.parametrize("variant,tile", [(0, 0), (3, 128), (4, 128), (3, 64), (4, 64), (3, 192), (4, 192)])
 def test_dgemm_mid_size_against_oracle(oracle, handle, variant, tile):
     # large enough for many CTAs and k-tiles, small enough for the long-double oracle (~1 s)
     handle.set_option("dgemm.variant", variant)
@@ -438,13 +438,15 @@ def test_dgemm_config5_column_block(handle):
     _full_size_vs_cublas(handle, np.float64, 0, 0, 8192, 1024, 8192, 9005)
 
 
-@pytest.mark.parametrize("tile,peel", [(64, 1), (128, 1), (128, 0)])
+@pytest.mark.parametrize("tile,peel", [(64, 1), (128, 1), (128, 0), (192, 1), (192, 0)])
 def test_dgemm_ragged_tiles_every_residue_class(handle, tile, peel):
-    """The consumers of a ragged tile skip the DMMA blocks (64x64 tiles) or whole warps (128x128) that lie outside C, and the
-    ragged tiles are scheduled after the full ones: residues on either side of every 8 / 16 / 32 / 64 boundary, both operand
-    orientations (8-row blocks for a K-contiguous operand, pairs of blocks for an M/N-contiguous one), k long enough for
-    the stream-K split (kt >= 8); C starts as NaN so an element nobody wrote is caught."""
+    """The consumers of a ragged tile skip the DMMA blocks (64x64 tiles) or whole warps (128x128, 128x64 = tile 192) that lie
+    outside C, and the ragged tiles are scheduled after the full ones: residues on either side of every 8 / 16 / 32 / 64
+    boundary, both operand orientations (8-row blocks for a K-contiguous operand, pairs of blocks for an M/N-contiguous one),
+    k long enough for the stream-K split (kt >= 8) and covering every k % 16 (the last k-tile skips the DMMA steps that see
+    no valid k); C starts as NaN so an element nobody wrote is caught."""
     handle.set_option("dgemm.tile", tile)
+    tile = 128 if tile == 192 else tile  # shapes below are sized in units of the larger tile edge
     handle.set_option("dgemm.peel", peel)  # 128x128 tiles: remainders of <= 16 rows / columns go to a second launch on 64x64 tiles
     try:
         res = [1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 57, 63, 65, 100, 127]
@@ -461,22 +463,73 @@ def test_dgemm_ragged_tiles_every_residue_class(handle, tile, peel):
 
 
 @pytest.mark.parametrize("ta,tb", OPS)
-def test_dgemm_thin_remainders_are_peeled_into_a_second_launch(oracle, handle, ta, tb):
-    """m % 128 or n % 128 in 1..16 on 128x128 tiles: the main launch covers the multiple of 128, 64x64-tile launches the
-    row strip (all columns) and the column strip (main rows); every element written once, alpha / beta honoured in each
-    piece, padding of C untouched, and the same result as the unpeeled kernel to within the bound."""
+@pytest.mark.parametrize("skinny", [1, 0], ids=["skinny", "strips64"])
+def test_dgemm_thin_remainders_are_peeled_into_a_second_launch(oracle, handle, ta, tb, skinny):
+    """m % 128 or n % 128 in 1..16 on 128x128 tiles (n % 64 on 128x64 tiles): the main launch covers the multiple of the tile,
+    the row strip (all columns) and the column strip (main rows) go to the skinny kernel (dgemm.skinny = 0: to launches on
+    64x64 tiles); every element written once, alpha / beta honoured in each piece, padding of C untouched, and the same
+    result as the unpeeled kernel to within the bound.  The four op pairs put both strips through both skinny kernels
+    (X contiguous along N / along K)."""
     handle.set_option("dgemm.tile", 128)
+    handle.set_option("dgemm.skinny", skinny)
+
+    def suffix(m, n, bn):  # strips up to 4 wide are the skinny kernel's, wider ones stay on 64x64 tiles
+        thin = [x for x in (m % 128, n % bn) if x]
+        return "+strips_skinny" if skinny and any(x <= 4 for x in thin) else "+strips64"
+
     try:
-        for (m, n, k, beta) in [(641, 528, 200, 0.0), (1025, 643, 96, -0.5), (520, 1033, 130, 1.0), (513, 512, 64, 0.0)]:
+        for (m, n, k, beta) in [(641, 528, 200, 0.0), (1025, 643, 96, -0.5), (520, 1033, 130, 1.0), (513, 512, 64, 0.0),
+                                (1040, 2049, 1111, 0.5), (2050, 517, 3000, 0.0)]:
             _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9500 + m, ldc_pad=3, nan_c=(beta == 0.0))
-            assert handle.last_kernel().endswith("+strips64"), handle.last_kernel()
+            assert handle.last_kernel().endswith(suffix(m, n, 128)), handle.last_kernel()
             handle.set_option("dgemm.peel", 0)
             _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9500 + m, ldc_pad=3, nan_c=(beta == 0.0))
             assert "strips" not in handle.last_kernel()
             handle.set_option("dgemm.peel", 1)
+        # odd leading dimensions and element-aligned bases reach the strips too
+        _gemm_case(oracle, handle, np.float64, ta, tb, 1025, 643, 333, -1.0, 0.25, 9590, lda_pad=1, ldb_pad=3, ldc_pad=1)
+        assert handle.last_kernel().endswith(suffix(1025, 643, 128)), handle.last_kernel()
+        # 128x64 tiles: m % 128 and n % 64 in 1..16 are the thin remainders
+        handle.set_option("dgemm.tile", 192)
+        for (m, n, k, beta) in [(641, 592, 200, 0.0), (1025, 579, 97, -0.5), (520, 1033, 130, 1.0), (640, 577, 73, 0.0)]:
+            _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9600 + m, ldc_pad=3, nan_c=(beta == 0.0))
+            assert "128x64" in handle.last_kernel() and handle.last_kernel().endswith(suffix(m, n, 64)), handle.last_kernel()
     finally:
         handle.set_option("dgemm.tile", 0)
         handle.set_option("dgemm.peel", 1)
+        handle.set_option("dgemm.skinny", 1)
+
+
+@pytest.mark.parametrize("ta,tb", OPS)
+def test_dgemm_gemv_shaped_calls_take_the_skinny_kernel(oracle, handle, ta, tb):
+    """C at most 4 rows or columns wide (and the other extent >= 256): the skinny kernel, both orientations of the large
+    operand, K cut into chunks whose partial sums are added in order (several chunks / a single one), alpha / beta, odd
+    leading dimensions, element-aligned bases; bit-identical when repeated."""
+    for (m, n, k, beta) in [(1, 3001, 2049, 0.0), (3, 700, 130, -0.5), (4, 260, 1000, 1.0), (2, 5000, 64, 0.0),
+                            (3001, 1, 2049, 0.0), (700, 4, 130, 0.5), (300, 2, 4097, 0.0), (5000, 3, 17, 1.0)]:
+        _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9700 + m + n, ldc_pad=3, nan_c=(beta == 0.0))
+        assert handle.last_kernel().startswith("dgemm_skinny_fma"), handle.last_kernel()
+        _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, -1.0, beta, 9800 + m + n, lda_pad=1, ldb_pad=3, ldc_pad=1, offset=1)
+        assert handle.last_kernel().startswith("dgemm_skinny_fma"), handle.last_kernel()
+    handle.set_option("dgemm.skinny", 0)
+    try:
+        _gemm_case(oracle, handle, np.float64, ta, tb, 1, 3001, 200, 1.5, 0.0, 9790)
+        assert "skinny" not in handle.last_kernel()
+    finally:
+        handle.set_option("dgemm.skinny", 1)
+    m, n, k = (2, 4100, 3000)
+    ar, ac = (k, m) if ta else (m, k)
+    br, bc = (n, k) if tb else (k, n)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand(ar * ac, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    B = torch.rand(br * bc, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    outs = []
+    for _ in range(20):
+        Cm = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+        handle.gemm(True, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+        outs.append(Cm)
+    assert handle.last_kernel().startswith("dgemm_skinny_fma")
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
 def test_dgemm_l2_eviction_hints_do_not_change_results(handle):

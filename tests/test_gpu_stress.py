@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 ITERS = 2000
 OPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
 # tile -> (m, n, k): 1024 tiles of that size, so every CTA walks a stream-K run and then data-parallel tiles
-SHAPES = {64: (4096, 1024, 1024), 128: (4096, 4096, 512)}
+SHAPES = {64: (4096, 1024, 1024), 128: (4096, 4096, 512), 192: (4096, 2048, 768)}  # 192 = 128x64 tiles
+TILE_NAMES = {64: "64x64", 128: "128x128", 192: "128x64"}
 
 
 def _operands(ta, tb, m, n, k, odd_ld, pattern=False):
@@ -50,7 +51,7 @@ def _stress(handle, tile, ta, tb, odd_ld, iters, pattern=False):
         C = C0.clone()
         handle.gemm(True, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
         kernel = handle.last_kernel()
-        assert f"{tile}x{tile}" in kernel and ("cpasync" in kernel) == bool(odd_ld), kernel
+        assert TILE_NAMES[tile] in kernel and ("cpasync" in kernel) == bool(odd_ld), kernel
         if pattern:
             T = k // 16
             ref = torch.full_like(C, 16.0 * T * (T - 1) / 2)
@@ -70,13 +71,13 @@ def _stress(handle, tile, ta, tb, odd_ld, iters, pattern=False):
 
 @pytest.mark.parametrize("ta,tb", OPS)
 @pytest.mark.parametrize("odd_ld", [0, 1], ids=["tma", "cpasync"])
-@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("tile", [64, 128, 192])
 def test_dgemm_repeats_bit_identically(handle, tile, odd_ld, ta, tb):
     _stress(handle, tile, ta, tb, odd_ld, ITERS)
 
 
 @pytest.mark.parametrize("ta,tb", [(1, 0), (0, 0)])
-@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("tile", [64, 128, 192])
 def test_dgemm_k_tile_pattern_is_exact(handle, tile, ta, tb):
     """exact answer known: no run may take a fragment from another k-tile (older or newer fill of its ring stage)"""
     _stress(handle, tile, ta, tb, 0, ITERS, pattern=True)

@@ -36,17 +36,17 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
     sc.col0[j] = j * nb;
     sc.cols[j] = (sc.col0[j] + nb > n) ? n - sc.col0[j] : nb;
   }
-  // The copy back of the last block is the one transfer nothing can hide.  Multi-GPU caller: the last block is halved.
-  // Single-GPU caller: it is tapered — halved again and again down to 256 columns (4096 -> 2048, 1024, 512, 256, 256) — each
-  // piece's copy back hides behind the next piece's product, which is still several times longer (config 5: the exposed
-  // tail goes from 537 MB to 67 MB, 10 ms to 1.3 ms).
+  // The copy back of the last block is the one transfer nothing can hide, so it is tapered — halved again and again down to
+  // 256 columns (4096 -> 2048, 1024, 512, 256, 256) — each piece's copy back hides behind the next piece's product, which is
+  // still several times longer (config 5: the exposed tail goes from 537 MB to 67 MB, 10 ms to 1.3 ms; where a product is
+  // shorter than a copy the copies simply queue up, as they would have untapered).  Column blocks are rank-local, so the
+  // multi-GPU caller tapers too (round 2's first version halved its last block once).
   while (blocks > 1 && sc.cols[blocks - 1] >= 512 && blocks < HostSchedule::BLOCK_CAP) {
     const int half = sc.cols[blocks - 1] / 2 / 128 * 128;
     sc.col0[blocks] = sc.col0[blocks - 1] + half;
     sc.cols[blocks] = sc.cols[blocks - 1] - half;
     sc.cols[blocks - 1] = half;
     blocks++;
-    if (multi) break;
   }
   int panels = 1, lead = 0;
   // The multi-GPU entry is collective: every rank must cut K into the SAME panels (the peers' "panel p has arrived" flags
@@ -91,6 +91,10 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
     // experiments: host.panels = -g forces the growing head with a growth of at least g per cent
     if (opt_panels < 0 && growth < -0.01 * opt_panels) growth = -0.01 * opt_panels;
   }
+  // Multi-GPU caller: the cuts are part of the collective contract, so the growth cannot follow this rank's column count.
+  // `lead` above carries a 1.3x margin of product over upload, which a growth of 0.2 stays inside; the head then starts at
+  // 256 k instead of half a regular panel (N = 8: 67 MB of this rank's share of A before the first product, 8 MB now).
+  if (multi && panels > 1 && opt_panels == 0) growth = 0.2;
   if ((growth >= 0.15 || opt_panels < 0) && kp >= 1024) {
     if (growth > 1.0) growth = 1.0;
     const int wmax = 4 * kp;

@@ -364,14 +364,27 @@ def main():
             return {"bound": "tensor", "achieved": achieved_tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_tf / DMMA_PEAK_TFLOPS,
                     "traffic": None, "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ms": k_ms,
                     "peak_source": "FP64 DMMA.8x8x4 issue peak measured on this pool (profiles/r01_probe_fp64_rates.txt); MEASURED_PEAKS.json has no FP64 entry"}
-        # config 4 sits at the HBM / tensor crossover: quote it against the HBM floor and give the tensor view alongside
+        # FP32 (3xTF32): the binding roof is whichever of the two floors is higher — the HBM floor (algorithmic bytes at the measured
+        # copy bandwidth) or the tensor floor (three TF32 products per useful one at the measured rate; MEASURED_PEAKS.json has a bf16
+        # figure, TF32 runs at half of it).  Config 4 (BASELINE.md calls it the bandwidth-bound regime) has an HBM floor of 0.339 ms
+        # and a tensor floor of 0.508 ms on this pool's measured peaks, so it is reported against the tensor roof with the HBM
+        # view alongside.
         gbs = alg_bytes / (k_ms * 1e-3) * 1e-9
         tf32x3 = peaks.get("bf16_tflops", 1590.0) / 2.0 / 3.0
+        t_hbm_ms = alg_bytes / (hbm_peak * 1e9) * 1e3
+        t_tensor_ms = 2.0 * m * n * k / (tf32x3 * 1e12) * 1e3
+        hbm_view = {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak, "floor_ms": t_hbm_ms,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+        tensor_view = {"achieved_tflops": achieved_tf, "peak_3xtf32_tflops": tf32x3, "frac": achieved_tf / tf32x3, "floor_ms": t_tensor_ms,
+                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32) / 3 (three split products per useful one)"}
+        if t_tensor_ms >= t_hbm_ms:
+            return {"bound": "tensor", "achieved": achieved_tf, "peak": tf32x3, "unit": "TFLOP/s", "frac": achieved_tf / tf32x3, "traffic": None,
+                    "algorithmic_bytes": alg_bytes, "algorithmic_flops": 2.0 * m * n * k, "kernel": kernel, "kernel_ms": k_ms,
+                    "hbm_view": hbm_view, "peak_source": tensor_view["peak_source"],
+                    "why_tensor": f"tensor floor {t_tensor_ms:.3f} ms > HBM floor {t_hbm_ms:.3f} ms at the measured peaks"}
         return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
-                "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ms": k_ms,
-                "tensor_view": {"achieved_tflops": achieved_tf, "peak_3xtf32_tflops": tf32x3, "frac": achieved_tf / tf32x3,
-                                "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32) / 3 (three split products per useful one)"},
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+                "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ms": k_ms, "tensor_view": tensor_view,
+                "peak_source": hbm_view["peak_source"]}
 
     def plan_gemm_alone(dtype, plan, ta, tb, m, n, k, A, B, Cm):
         """The GEMM launch the chosen plan makes, alone: operands moved (transposed / padded to ld % 32 == 0) as the plan's

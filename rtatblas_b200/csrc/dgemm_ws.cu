@@ -96,6 +96,7 @@ struct Params {
   // rows of op(A) / columns of op(B) the operand's 3-D map covers (see tma_load_3d; 0 = no 3-D map): a tile wholly below
   // the limit is ONE box per stage, the ragged last tile row / column takes the 2-D boxes
   int a_3d, b_3d;
+  int group;       // grouped raster: tile rows per sweep across n
   int tail_steps;  // DMMA steps of the last k-tile that see a valid k (1..4; 4 when k is a multiple of 16): see mma_ktile
   int prefetch_c;  // beta != 0: consumers prefetch their part of the C tile into L2 when the tile starts (option dgemm.prefetch_c)
 };
@@ -422,7 +423,7 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       n0 = (tile < p.e_row ? tile : p.tn_full) * BN;
       return;
     }
-    constexpr int GROUP = 8;
+    const int GROUP = p.group;  // tile rows swept together across the columns (option dgemm.group, default 8)
     int group_size = GROUP * p.tn_full;
     int first_m = (tile / group_size) * GROUP;
     int gm = min(p.tm_full - first_m, GROUP);
@@ -869,6 +870,8 @@ static int run_cfg(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, 
     p.sk_generation = ++h->sk_generation;
   }
   p.prefetch_c = opt(h, "dgemm.prefetch_c", 1);
+  p.group = opt(h, "dgemm.group", 8);
+  if (p.group < 1) p.group = 1;
   const bool hints = !tri && opt(h, "dgemm.l2_hints", 0) != 0;
   p.l2_a = hints ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   p.l2_b = hints ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
@@ -954,7 +957,14 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
     // operands hot in L2 from the pad pass: 64x64 1.453 ms, 128x128 + strip 1.470; cold: 1.527 against 1.496)
     const bool l2_resident = 8.0 * ((double)m * k + (double)k * n) < 0.95 * (double)h->l2_bytes;
     if ((peeled(m, 128) != m || peeled(n, 128) != n) && l2_resident) t128 *= 1.03;
-    tile_cfg = (small || (t64 < t128 && t64 < tmid)) ? 64 : (tmid < t128 ? 192 : 128);
+    // few tiles and a long k (512 x 512 x 16384: 16 tiles of 128x128): the finer cut gives every CTA a shorter fix-up
+    const bool few = (long long)((m + 127) / 128) * ((n + 127) / 128) <= h->sm_count / 4;
+    // ... unless the 64x64 tiles would be ragged: their block-granular edge loop is the slower code (1000^3: 82 us against
+    // 76 on 128x64 tiles; 1024^3: 71 against 77)
+    const bool ragged64 = (m % 64 != 0 || n % 64 != 0) && tmid < 1e300 && m >= 256 && n >= 256;
+    if ((small || few) && !ragged64) tile_cfg = 64;
+    else if (small || few) tile_cfg = 192;
+    else tile_cfg = (t64 < t128 && t64 < tmid) ? 64 : (tmid < t128 ? 192 : 128);
   }
   if (tile_cfg == 64)
     return run_cfg<ws::Cfg64>(h, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, allow_tma, "64x64x16", tri);

@@ -148,14 +148,16 @@ geam_stream256_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T
 template <typename T, int MODE, bool VEC, int UNR>
 __global__ void __launch_bounds__(256)
 geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T beta, const T *B, int ldb, T *C, int ldc,
-                   int chunks_per_col) {
+                   int chunks_per_col, int chunk_len) {
   constexpr int VN = VEC ? Vec16<T>::N : 1;
-  constexpr int CHUNK = 256 * VN * UNR;
   using V = typename Vec16<T>::type;
   const long long total = (long long)chunks_per_col * n;
   for (long long w = blockIdx.x; w < total; w += gridDim.x) {
     const int j = int(w / chunks_per_col);
-    const int i0 = int(w % chunks_per_col) * CHUNK + threadIdx.x * VN;
+    // chunk_len <= 256 * VN * UNR elements of the column, the same for every chunk (the dispatcher cuts a column into equal
+    // parts: m = 4097 on 2048-element chunks left every third CTA a single element)
+    const int i0 = int(w % chunks_per_col) * chunk_len + threadIdx.x * VN;
+    const int m_end = min(m, int(w % chunks_per_col) * chunk_len + chunk_len);
     const T *a = A + (size_t)j * lda, *b = B + (size_t)j * ldb;
     T *c = C + (size_t)j * ldc;
     if (VEC) {
@@ -163,7 +165,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
 #pragma unroll
       for (int u = 0; u < UNR; u++) {
         const int i = i0 + u * 256 * VN;
-        if (i < m) {  // m % VN == 0 is guaranteed by the dispatcher for the vector path
+        if (i < m_end) {  // m % VN == 0 and chunk_len % VN == 0 are guaranteed by the dispatcher for the vector path
           if (MODE != 1) va[u] = __ldcs(reinterpret_cast<const V *>(a + i));
           if (MODE != 0) vb[u] = *reinterpret_cast<const V *>(b + i);
         }
@@ -171,7 +173,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
 #pragma unroll
       for (int u = 0; u < UNR; u++) {
         const int i = i0 + u * 256 * VN;
-        if (i < m) {
+        if (i < m_end) {
           V out;
           T *o = reinterpret_cast<T *>(&out);
           const T *pa = reinterpret_cast<const T *>(&va[u]);
@@ -186,7 +188,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
 #pragma unroll
       for (int u = 0; u < UNR; u++) {
         const int i = i0 + u * 256;
-        if (i < m) {
+        if (i < m_end) {
           if (MODE != 1) va[u] = __ldcs(a + i);
           if (MODE != 0) vb[u] = b[i];
         }
@@ -194,7 +196,7 @@ geam_stream_kernel(int m, int n, T alpha, const T *__restrict__ A, int lda, T be
 #pragma unroll
       for (int u = 0; u < UNR; u++) {
         const int i = i0 + u * 256;
-        if (i < m) __stcs(c + i, axpby<T, MODE>(alpha, MODE != 1 ? va[u] : T(0), beta, MODE != 0 ? vb[u] : T(0)));
+        if (i < m_end) __stcs(c + i, axpby<T, MODE>(alpha, MODE != 1 ? va[u] : T(0), beta, MODE != 0 ? vb[u] : T(0)));
       }
     }
   }
@@ -431,17 +433,20 @@ static int launch_geam(rtat_b200_context *h, int transa, int transb, int m, int 
         return go(std::integral_constant<int, 1>{}, 1 << 20, std::integral_constant<int, 0>{});
       }
     }
-    const int chunk = 256 * (vec ? VN * UNR_V : UNR_S);
-    const int chunks_per_col = (m + chunk - 1) / chunk;
+    const int chunk_max = 256 * (vec ? VN * UNR_V : UNR_S);
+    const int chunks_per_col = (m + chunk_max - 1) / chunk_max;
+    // equal parts of a column, rounded up to whole warps of vectors
+    const int gran = 32 * (vec ? VN : 1);
+    const int chunk_len = opt(h, "geam.even_chunks", 1) ? ((m + chunks_per_col - 1) / chunks_per_col + gran - 1) / gran * gran : chunk_max;
     const long long total = (long long)chunks_per_col * n;
     // one chunk per CTA (see the 32-byte path above); geam.persistent = 1 restores the grid-stride walk over 8 CTAs per SM
     const long long cap = opt(h, "geam.persistent") ? (long long)max_ctas : 0x7fffffffLL;
     const int grid = (int)(total < cap ? total : cap);
     if (vec) {
-      geam_stream_kernel<T, MODE, true, UNR_V><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col);
+      geam_stream_kernel<T, MODE, true, UNR_V><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col, chunk_len);
       return check_launch(h, "geam_stream_vec16");
     }
-    geam_stream_kernel<T, MODE, false, UNR_S><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col);
+    geam_stream_kernel<T, MODE, false, UNR_S><<<grid, 256, 0, s>>>(m, n, alpha, A, lda, beta, B, ldb, C, ldc, chunks_per_col, chunk_len);
     return check_launch(h, "geam_stream_scalar");
   }
   const int TL = (ta && tb) ? 32 : 64;

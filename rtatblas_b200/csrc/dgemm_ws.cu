@@ -935,8 +935,8 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
       return sixteenths / 16.0 * bm * bn;
     };
     // measured steady-state efficiencies: TMA producers 0.985 / 0.96 (128 / 64 tiles); cp.async producers 0.92 / 0.85
-    // the peeled strips ride along at the 64x64 rate plus ~5 us of fixed cost per launch (as C area: t x rate / 2k)
-    const double launch_area = 5e-6 * 36e12 / (2.0 * (k > 0 ? k : 1));
+    // the peeled strips ride along at the 64x64 rate plus ~8 us of fixed cost per strip (as C area: t x rate / 2k)
+    const double launch_area = 8e-6 * 36e12 / (2.0 * (k > 0 ? k : 1));
     auto with_strips = [&](int bm, int bn, double eff) {
       const int mm = peeled(m, bm), nn = peeled(n, bn);
       double strips = (mm != m || nn != n) ? (padded(64, 64, m - mm, n) + padded(64, 64, mm, n - nn)) / (tma ? 0.96 : 0.85) + launch_area * ((mm != m) + (nn != n)) : 0.0;
@@ -962,8 +962,9 @@ int dgemm_ws(rtat_b200_context *h, bool ta, bool tb, int m, int n, int k, double
     // ... unless the 64x64 tiles would be ragged: their block-granular edge loop is the slower code (1000^3: 82 us against
     // 76 on 128x64 tiles; 1024^3: 71 against 77)
     const bool ragged64 = (m % 64 != 0 || n % 64 != 0) && tmid < 1e300 && m >= 256 && n >= 256;
-    if ((small || few) && !ragged64) tile_cfg = 64;
-    else if (small || few) tile_cfg = 192;
+    // (a peeled strip is one or two more launches: the estimates carry their fixed cost, which decides the K-panel products
+    // of the host pipeline — 4097 x 384 x 512 stays on 64x64 tiles)
+    if (small || few) tile_cfg = (ragged64 && tmid < 1.05 * t64) ? 192 : 64;
     else tile_cfg = (t64 < t128 && t64 < tmid) ? 64 : (tmid < t128 ? 192 : 128);
   }
   if (tile_cfg == 64)

@@ -62,6 +62,11 @@ inline HostSchedule plan_host_schedule(int m, int n, int k, size_t elem, size_t 
     // depths, so the multi-GPU caller gets a margin: one leading block at N = 4 measured 0.934 of the HBM-resident rate
     lead = t_mm > t_b ? (multi ? int(1.3 * t_a / (t_mm - t_b)) + 1 : int(t_a / (t_mm - t_b) + 0.5)) : blocks;
     if (lead < 1) lead = 1;
+    // Copy-back bound problems (config 3: 98 MB of C leave in 1.8 ms, the whole product takes 1.45): the copies back must start
+    // as early as possible, i.e. some column block must be COMPLETE early, and a leading block is complete only when all of A
+    // is up.  Two leading blocks carry the K-panel phase, the rest follow whole-K with their copies back behind them (config 3
+    // end to end 4.12 -> 3.52 ms with every block leading; 1 block: 3.58, 4 blocks: 3.63).
+    if (!multi && double(elem) * m * n / pcie_rate > 0.75 * (2.0 * m * double(n) * k / rate) && lead > 2) lead = 2;
     if (opt_panels > 0) panels = opt_panels < MAX_PANELS ? opt_panels : MAX_PANELS;
     if (opt_lead > 0) lead = opt_lead;
     if (lead > blocks) lead = blocks;

@@ -64,9 +64,10 @@ def test_baseline_config_schedules_match_the_design_notes():
     # the override keeps round 2's first schedule reachable: 8 panels of 1024 with the first one halved, 4 leading blocks
     sc = rt.host_schedule(8, 1, 8192, 8192, 8192, 8192, panels=8, lead=4)
     assert sc["panels"] == [(0, 512), (512, 512)] + [(1024 * i, 1024) for i in range(1, 8)] and sc["lead"] == 4
-    # config 3 (4097 x 3001 x 2049, op NT): every block is a leading one (the transfer of A dominates)
+    # config 3 (4097 x 3001 x 2049, op NT): the transfer of A dominates the upload, but the copy back of C (98 MB) outlasts the
+    # whole product, so only two blocks lead (a leading block is complete, and its copy back can start, only when all of A is up)
     sc = rt.host_schedule(8, 0, 4097, 3001, 2049, 4097)
-    assert sc["lead"] == len(sc["blocks"]) and len(sc["panels"]) == 3
+    assert sc["lead"] == 2 and len(sc["blocks"]) == 8 and len(sc["panels"]) == 3
     # config 5 on one GPU: one leading block whose product is 1.4x its panel's upload -> a head growing from 256 k by 0.37 of
     # what is already up (no longer capped at the regular 4096), and a tail tapered from 4096 columns down to 256
     sc = rt.host_schedule(8, 0, 32768, 32768, 32768, 32768)

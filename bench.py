@@ -517,6 +517,38 @@ def main():
         planner.close()
         return out, (A, B, Cm, ar, br)
 
+    def config_e2e(name, bufs):
+        """the same GEMM through the host-buffer entry point of the C ABI: pinned host buffers, H2D + GEMM + D2H timed"""
+        dtype, ta_s, tb_s, m, n, k = CONFIGS[name]
+        ta, tb, dbl = int(ta_s == "T"), int(tb_s == "T"), dtype == "double"
+        A, B, Cm, ar, br = bufs
+        esz = A.element_size()
+        hA = torch.empty(A.numel(), dtype=A.dtype, pin_memory=True)
+        hB = torch.empty(B.numel(), dtype=B.dtype, pin_memory=True)
+        hC = torch.empty(m * n, dtype=A.dtype, pin_memory=True)
+        hA.copy_(A)
+        hB.copy_(B)
+        torch.cuda.synchronize()
+        fn = lambda: handle.gemm(dbl, ta, tb, m, n, k, 1.0, hA, ar, hB, br, 0.0, hC, m, host=True)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        # the result that crossed PCIe, against the device-side result of the planner's step (same inputs): sampled entries
+        idx = torch.randint(0, m * n, (4096,), generator=torch.Generator().manual_seed(7))
+        dev = Cm[idx.cuda()].cpu().to(torch.float64)
+        got = hC[idx].to(torch.float64)
+        rel = float(((got - dev).abs().max() / dev.abs().max().clamp_min(1e-300)).item())
+        return {"value": 2.0 * m * n * k / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms, "steps": reps,
+                "h2d_bytes_per_step": (A.numel() + B.numel()) * esz, "d2h_bytes_per_step": m * n * esz,
+                "api": f"rtat_b200_{'d' if dbl else 's'}gemm_host (pinned host buffers)",
+                "max_rel_diff_vs_device_result": rel}
+
     def bench_moves():
         """matrix_ops through the C ABI (what MatrixMove calls): GB/s of 2 rows cols sizeof(T) algorithmic bytes"""
         res = {}
@@ -732,6 +764,8 @@ def main():
         plan_steps = {"c1": 50, "c2": 10, "c3": 20, "c4": 20}
         for name in ("c1", "c2", "c3", "c4"):
             res, _bufs = bench_config(name, plan_steps[name], 3, 1 if name == "c3" else 3)
+            if not args.no_e2e:
+                res["e2e"] = config_e2e(name, _bufs)
             del _bufs
             torch.cuda.empty_cache()
             per[name] = res

@@ -397,6 +397,11 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
+  if (USE_TMA && threadIdx.x == CONSUMER_WARPS * 32) {
+    // descriptors into the TMA unit's cache while the barriers are being set up, before the first load asks for them
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(KCA || p.a_3d == 0 ? &mapA : &mapA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(KCB || p.b_3d == 0 ? &mapB : &mapB3) : "memory");
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
@@ -593,7 +598,9 @@ dgemm_ws_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           __stcg(slot + ((i * NI + j) * 2 + 0) * (CONSUMER_WARPS * 32), acc[i][j][0]);
           __stcg(slot + ((i * NI + j) * 2 + 1) * (CONSUMER_WARPS * 32), acc[i][j][1]);
         }
-      __threadfence();
+      // publication: the consumers' barrier orders every thread's stores before thread 0's release at GPU scope (releases
+      // are cumulative over what happens-before them), so no thread needs a fence of its own — a MEMBAR.SC.GPU per thread
+      // in round 1
       asm volatile("bar.sync 1, %0;\n" ::"n"(CONSUMER_WARPS * 32) : "memory");
       if (ctid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p.sk_flags + blockIdx.x), "r"(p.sk_generation) : "memory");
       continue;

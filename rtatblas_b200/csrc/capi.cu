@@ -113,6 +113,7 @@ int rtat_b200_destroy(rtat_b200_handle_t h) {
   if (h->trsm_inv) cudaFree(h->trsm_inv);
   if (h->sgemm_a_pad) cudaFree(h->sgemm_a_pad);
   if (h->sk_flags) cudaFree(h->sk_flags);
+  if (h->skinny_counters) cudaFree(h->skinny_counters);
   if (h->order_event) cudaEventDestroy(h->order_event);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);

@@ -36,6 +36,8 @@ struct rtat_b200_context {
   // stream-K fix-up flags (1024 x u32) and the generation they are compared against
   void *sk_flags = nullptr;
   unsigned sk_generation = 0;
+  // skinny DGEMM: arrival counters of the column blocks (zero between launches)
+  void *skinny_counters = nullptr;
   // host-entry staging
   void *staging = nullptr;
   size_t staging_bytes = 0;

@@ -18,8 +18,9 @@
 //                                     per load) and the r x JW sums are folded with shuffles.
 //
 // K is cut into chunks, one CTA per (column block, chunk), so that a strip a few thousand columns wide still fills the
-// machine; partial sums go to the handle's arena and a second small kernel adds them IN CHUNK ORDER (deterministic, like
-// the stream-K fix-up) and applies alpha / beta.  One chunk: the first kernel finishes Y itself.
+// machine; partial sums go to the handle's arena and the LAST CTA of a column block to arrive (a counter per block) adds
+// them IN CHUNK ORDER — deterministic whoever is last, like the stream-K fix-up — and applies alpha / beta.  One chunk:
+// the CTA finishes Y itself.  (Round 2's first version reduced in a second launch: 3 us of a 15 us strip.)
 #include "common.cuh"
 
 namespace rtat_b200 {
@@ -38,24 +39,43 @@ struct Params {
   long long ys_i, ys_j;
   double alpha, beta;
   int kc, nchunks, jblocks;
-  double *partial;  // [nchunks][R][N] when nchunks > 1
+  double *partial;     // [nchunks][R][N] when nchunks > 1
+  unsigned *counters;  // one per column block, zero between launches: the CTA that finds nchunks - 1 adds the partial sums
 };
 
 constexpr int THREADS = 128;
 constexpr int SKINNY_MAX_ROWS = 4;
+constexpr int MAX_COUNTERS = 4096;
 
-// S chunk -> shared memory, zero beyond the strip's r rows and the chunk's valid k.  The faster index follows S's
-// contiguous direction.
-template <int R, int KC, bool K_MAJOR /* sm[kk][i] (true) or sm[i][kk] */>
-__device__ __forceinline__ void load_s(double *sm, const Params &p, int k0, int kc) {
-  for (int idx = threadIdx.x; idx < R * KC; idx += THREADS) {
-    int i, kk;
-    if (p.ss_k == 1) { kk = idx % KC; i = idx / KC; } else { i = idx % R; kk = idx / R; }
-    double v = 0.0;
-    if (i < p.r && kk < kc) v = p.S[i * p.ss_i + (long long)(k0 + kk) * p.ss_k];
-    sm[K_MAJOR ? kk * R + i : i * KC + kk] = v;
+// S tile: R x KC elements, zero beyond the strip's r rows and the unit's valid k.  A thread's share is fetched into
+// registers one unit ahead (the global latency of the tile would otherwise sit between every two units: a CTA computes a
+// unit in a few hundred cycles) and stored into the other of two shared-memory buffers.  The faster index of the fetch
+// follows S's contiguous direction.
+template <int R, int KC>
+struct STile {
+  static constexpr int PER = (R * KC + THREADS - 1) / THREADS;
+  double v[PER];
+  __device__ __forceinline__ void fetch(const Params &p, int k0, int k_end) {
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+      const int idx = threadIdx.x + t * THREADS;
+      int i, kk;
+      if (p.ss_k == 1) { kk = idx % KC; i = idx / KC; } else { i = idx % R; kk = idx / R; }
+      v[t] = 0.0;
+      if (idx < R * KC && i < p.r && k0 + kk < k_end) v[t] = __ldg(p.S + i * p.ss_i + (long long)(k0 + kk) * p.ss_k);
+    }
   }
-}
+  template <bool K_MAJOR /* sm[kk][i] (true) or sm[i][kk] */>
+  __device__ __forceinline__ void store(const Params &p, double *sm) const {
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+      const int idx = threadIdx.x + t * THREADS;
+      int i, kk;
+      if (p.ss_k == 1) { kk = idx % KC; i = idx / KC; } else { i = idx % R; kk = idx / R; }
+      if (idx < R * KC) sm[K_MAJOR ? kk * R + i : i * KC + kk] = v[t];
+    }
+  }
+};
 
 __device__ __forceinline__ void finish(const Params &p, int i, int j, double sum) {
   double *y = p.Y + i * p.ys_i + j * p.ys_j;
@@ -64,10 +84,45 @@ __device__ __forceinline__ void finish(const Params &p, int i, int j, double sum
   *y = v;
 }
 
+// sum of output (i, j) over the chunks, in chunk order; loads in batches of 8 (one memory latency per batch, not per chunk)
+template <int R>
+__device__ __forceinline__ double ordered_sum(const Params &p, int i, int j) {
+  const double *src = p.partial + (size_t)i * p.N + j;
+  const size_t step = (size_t)R * p.N;
+  double sum = 0.0;
+  int c = 0;
+  for (; c + 8 <= p.nchunks; c += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (size_t)(c + u) * step);
+#pragma unroll
+    for (int u = 0; u < 8; u++) sum += v[u];
+  }
+  for (; c < p.nchunks; c++) sum += __ldcg(src + (size_t)c * step);
+  return sum;
+}
+
+// After a CTA has stored its partial sums: the last of a column block's nchunks CTAs to arrive adds them up — in chunk
+// order whoever it is, so the result does not depend on the arrival order — and resets the counter for the next launch.
+__device__ __forceinline__ bool last_of_column_block(const Params &p, int jb) {
+  __shared__ unsigned arrived;
+  if (!p.counters) return false;  // separate reduction kernel (more column blocks than counters)
+  __threadfence();   // this thread's partial sums before the counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    arrived = atomicAdd(p.counters + jb, 1u);
+    if (arrived == (unsigned)p.nchunks - 1) p.counters[jb] = 0;
+  }
+  __syncthreads();
+  const bool last = arrived == (unsigned)p.nchunks - 1;
+  if (last) __threadfence();  // the other CTAs' partial sums after the counter
+  return last;
+}
+
 // ---- X contiguous along N ---------------------------------------------------------------------------------------
-template <int R, int KC>
+template <int R, int KC, bool PIPE>
 __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
-  __shared__ __align__(16) double sm[KC * R];
+  __shared__ __align__(16) double sm[PIPE ? 2 : 1][KC * R];
   const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
   const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
   const int j = jb * THREADS + threadIdx.x;
@@ -75,11 +130,21 @@ __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
   double acc[R];
 #pragma unroll
   for (int i = 0; i < R; i++) acc[i] = 0.0;
-  for (int k0 = k_begin; k0 < k_end; k0 += KC) {
+  STile<R, KC> next;
+  if (PIPE) next.fetch(p, k_begin, k_end);
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += KC, buf ^= PIPE ? 1 : 0) {
     const int kc = min(KC, k_end - k0);
-    __syncthreads();  // the previous unit's S tile has been read
-    load_s<R, KC, true>(sm, p, k0, kc);
-    __syncthreads();
+    if (PIPE) {
+      next.template store<true>(p, sm[buf]);
+      __syncthreads();  // one barrier per unit: buffer `buf` was last read two units ago
+      if (k0 + KC < k_end) next.fetch(p, k0 + KC, k_end);
+    } else {
+      __syncthreads();  // the previous unit's tile has been read
+      next.fetch(p, k0, k_end);
+      next.template store<true>(p, sm[0]);
+      __syncthreads();
+    }
     if (!active) continue;
     const double *xp = p.X + (long long)k0 * p.xs_k + j;
     constexpr int U = R <= 2 ? 16 : 8;  // loads in flight per thread: a GEMV lives on memory-level parallelism
@@ -90,22 +155,31 @@ __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
 #pragma unroll
       for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int i = 0; i < R; i++) acc[i] = fma(sm[(kk + u) * R + i], x[u], acc[i]);  // rows of sm beyond kc are zero
+        for (int i = 0; i < R; i++) acc[i] = fma(sm[buf][(kk + u) * R + i], x[u], acc[i]);  // rows of sm beyond kc are zero
     }
   }
-  if (!active) return;
+  if (p.nchunks == 1) {
+    if (!active) return;
 #pragma unroll
-  for (int i = 0; i < R; i++) {
-    if (i >= p.r) break;
-    if (p.nchunks == 1) finish(p, i, j, acc[i]);
-    else __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[i]);
+    for (int i = 0; i < R; i++)
+      if (i < p.r) finish(p, i, j, acc[i]);
+    return;
   }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < R; i++)
+      if (i < p.r) __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[i]);
+  }
+  if (!last_of_column_block(p, jb) || !active) return;
+#pragma unroll
+  for (int i = 0; i < R; i++)
+    if (i < p.r) finish(p, i, j, ordered_sum<R>(p, i, j));
 }
 
 // ---- X contiguous along K ---------------------------------------------------------------------------------------
-template <int R, int KC, int JW>
+template <int R, int KC, int JW, bool PIPE>
 __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
-  __shared__ __align__(16) double sm[R * KC];
+  __shared__ __align__(16) double sm[PIPE ? 2 : 1][R * KC];
   const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
   const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -119,11 +193,21 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
   const double *xp[JW];
 #pragma unroll
   for (int jj = 0; jj < JW; jj++) xp[jj] = p.X + (long long)min(j0 + jj, p.N - 1) * p.xs_j;  // clamped: never stored
-  for (int k0 = k_begin; k0 < k_end; k0 += KC) {
+  STile<R, KC> next;
+  if (PIPE) next.fetch(p, k_begin, k_end);
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += KC, buf ^= PIPE ? 1 : 0) {
     const int kc = min(KC, k_end - k0);
-    __syncthreads();
-    load_s<R, KC, false>(sm, p, k0, kc);
-    __syncthreads();
+    if (PIPE) {
+      next.template store<false>(p, sm[buf]);
+      __syncthreads();
+      if (k0 + KC < k_end) next.fetch(p, k0 + KC, k_end);
+    } else {
+      __syncthreads();
+      next.fetch(p, k0, k_end);
+      next.template store<false>(p, sm[0]);
+      __syncthreads();
+    }
     if (!active) continue;
 #pragma unroll
     for (int t = 0; t < KC / 32; t++) {
@@ -133,56 +217,57 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
       for (int jj = 0; jj < JW; jj++) x[jj] = kk < kc ? __ldg(xp[jj] + k0 + kk) : 0.0;
 #pragma unroll
       for (int i = 0; i < R; i++) {
-        const double sv = sm[i * KC + kk];
+        const double sv = sm[buf][i * KC + kk];
 #pragma unroll
         for (int jj = 0; jj < JW; jj++) acc[jj][i] = fma(sv, x[jj], acc[jj][i]);
       }
     }
   }
-  if (!active) return;
+  if (active) {
 #pragma unroll
-  for (int jj = 0; jj < JW; jj++)
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-      double v = acc[jj][i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[jj][i] = v;
-    }
-  if (lane == 0) {
-#pragma unroll
-    for (int jj = 0; jj < JW; jj++) {
-      const int j = j0 + jj;
-      if (j >= p.N) break;
+    for (int jj = 0; jj < JW; jj++)
 #pragma unroll
       for (int i = 0; i < R; i++) {
-        if (i >= p.r) break;
-        if (p.nchunks == 1) finish(p, i, j, acc[jj][i]);
-        else __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[jj][i]);
+        double v = acc[jj][i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[jj][i] = v;
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int jj = 0; jj < JW; jj++) {
+        const int j = j0 + jj;
+        if (j < p.N) {
+#pragma unroll
+          for (int i = 0; i < R; i++) {
+            if (i < p.r) {
+              if (p.nchunks == 1) finish(p, i, j, acc[jj][i]);
+              else __stcg(p.partial + ((size_t)chunk * R + i) * p.N + j, acc[jj][i]);
+            }
+          }
+        }
       }
     }
   }
+  if (p.nchunks == 1) return;
+  if (!last_of_column_block(p, jb)) return;
+  // this CTA's (THREADS / 32) * JW columns x r rows: one output per thread
+  constexpr int COLS = (THREADS / 32) * JW;
+  for (int o = threadIdx.x; o < COLS * R; o += THREADS) {
+    const int i = o / COLS, j = jb * COLS + o % COLS;
+    if (i < p.r && j < p.N) finish(p, i, j, ordered_sum<R>(p, i, j));
+  }
 }
 
-// partial sums -> Y, chunks added in order
+// partial sums -> Y, chunks added in order: the fallback when a launch has more column blocks than counters
 __global__ void __launch_bounds__(THREADS) skinny_reduce_kernel(const Params p, int R) {
   const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
   if (idx >= (long long)p.r * p.N) return;
   const int i = int(idx / p.N), j = int(idx % p.N);
-  // loads in batches of 8 (one memory latency per batch, not per chunk: 33 chunks cost 12.7 us one by one — ncu, config 3's
-  // strip), added in chunk order
   const double *src = p.partial + (size_t)i * p.N + j;
   const size_t step = (size_t)R * p.N;
   double sum = 0.0;
-  int c = 0;
-  for (; c + 8 <= p.nchunks; c += 8) {
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (size_t)(c + u) * step);
-#pragma unroll
-    for (int u = 0; u < 8; u++) sum += v[u];
-  }
-  for (; c < p.nchunks; c++) sum += __ldcg(src + (size_t)c * step);
+  for (int c = 0; c < p.nchunks; c++) sum += __ldcg(src + (size_t)c * step);
   finish(p, i, j, sum);
 }
 
@@ -205,18 +290,41 @@ static int run(rtat_b200_context *h, Params p) {
   if (nchunks < 1) nchunks = 1;
   p.kc = ((units + nchunks - 1) / nchunks) * KC;
   p.nchunks = (p.K + p.kc - 1) / p.kc;
+  bool fused = true;
   if (p.nchunks > 1) {
     const size_t bytes = sizeof(double) * (size_t)p.nchunks * R * p.N;
     if (bytes > (size_t(256) << 20)) return RTAT_B200_STATUS_NOT_SUPPORTED;
     if (int st = ensure_arena(h, bytes)) return st;
     p.partial = static_cast<double *>(h->arena);
+    fused = p.jblocks <= MAX_COUNTERS && opt(h, "dgemm.skinny_fused", 1) != 0;
+    if (fused && !h->skinny_counters) {
+      if (cudaMalloc(&h->skinny_counters, MAX_COUNTERS * sizeof(unsigned)) != cudaSuccess ||
+          cudaMemsetAsync(h->skinny_counters, 0, MAX_COUNTERS * sizeof(unsigned), h->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return RTAT_B200_STATUS_ALLOC_FAILED;
+      }
+    }
+    p.counters = fused ? static_cast<unsigned *>(h->skinny_counters) : nullptr;
   }
   const long long grid = (long long)p.jblocks * p.nchunks;
   if (grid > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  if (xj) skinny_xj_kernel<R, KCJ><<<(unsigned)grid, THREADS, 0, h->stream>>>(p);
-  else skinny_xk_kernel<R, KCK, JW><<<(unsigned)grid, THREADS, 0, h->stream>>>(p);
+  const Params &pk = p;
+  // S tile fetched one unit ahead into a second buffer (PIPE) or in place between two barriers: option dgemm.skinny_pipe
+  // (0 = choose, 1 / 2 = on / off)
+  const int units_per_cta = p.kc / KC;
+  int pipe = opt(h, "dgemm.skinny_pipe", 0);
+  // measured (probe/perf_gemv_vs_cublas.py, us, on / off): N-contiguous X 1 x 8192 x 4096 54.5 / 53.5, 4 x 8192 x 4096 79 / 136,
+  // 8192 x 4 x 2048 44 / 72; K-contiguous X 1 x 8192 x 2048 58 / 37, 4 x 8192 x 2048 51 / 54, 32768 x 2 x 32768 1389 / 1763
+  if (pipe == 0) pipe = (xj || R >= 4 || units_per_cta >= 32) ? 1 : 2;
+  if (xj) {
+    if (pipe == 1) skinny_xj_kernel<R, KCJ, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    else skinny_xj_kernel<R, KCJ, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+  } else {
+    if (pipe == 1) skinny_xk_kernel<R, KCK, JW, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    else skinny_xk_kernel<R, KCK, JW, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+  }
   int st = check_launch(h, xj ? "dgemm_skinny_fma_xn" : "dgemm_skinny_fma_xk");
-  if (st || p.nchunks == 1) return st;
+  if (st || p.nchunks == 1 || fused) return st;
   const long long outs = (long long)p.r * p.N;
   skinny_reduce_kernel<<<(unsigned)((outs + THREADS - 1) / THREADS), THREADS, 0, h->stream>>>(p, R);
   return check_launch(h, xj ? "dgemm_skinny_fma_xn+reduce" : "dgemm_skinny_fma_xk+reduce");

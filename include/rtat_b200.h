@@ -136,6 +136,9 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *     dgemm.tile [0]            128 / 64 / 192 (= 128x64 tiles): force the tile configuration of the persistent DGEMM
  *     dgemm.mid [1]             0: the automatic choice never takes 128x64 tiles
  *     dgemm.skinny [1]          0: thin strips and GEMV-shaped calls (at most 4 rows / columns of C) stay on the tile kernels
+ *     dgemm.skinny_fused [1]    0: the skinny kernel's partial sums are added by a second launch instead of the last CTA
+ *     dgemm.skinny_pipe [0]     1 / 2: S tiles of the skinny kernel fetched one tile ahead always / never (0 = by shape)
+ *     dgemm.group [8]           tile rows the grouped raster of the persistent DGEMM sweeps across n together
  *     dgemm.ktail [1]           0: the last k-tile of a k that is not a multiple of 16 runs all four DMMA steps
  *     dgemm.streamk [1]         0: data-parallel schedule only
  *     dgemm.tma3d [1]           0: eight 2-D TMA boxes per M/N-contiguous operand stage instead of one 3-D box
@@ -150,6 +153,7 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *     geam.transpose [0]        transposing geam: 1 = TMA pipeline, 2 = register-blocked kernel (the default choice),
  *                               3 = scalar tile kernel; geam.order = 1 / geam.upc = 2: CTA order / tile height of kernel 2
  *     geam.persistent [0]       1: grid-stride streaming copies on 8 CTAs per SM instead of one chunk per CTA
+ *     geam.even_chunks [1]      0: fixed 2048-element (16 B vectors: 2048-vector) chunks instead of equal parts of a column
  *     geam.force_cpasync [0]    1: cp.async producers in the TMA transposer even for a TMA-addressable source
  *     geam.tune, geam.rounding  launch-shape and rounding experiments of geam (see csrc/geam.cu)
  *     trsm.base [0]             diagonal-block size of the recursive TRSM (0 = 128)

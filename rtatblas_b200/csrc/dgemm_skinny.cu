@@ -29,17 +29,18 @@ int ensure_arena(rtat_b200_context *h, size_t bytes);
 
 namespace skinny {
 
+template <typename T>
 struct Params {
   int r, N, K;
-  const double *S;
+  const T *S;
   long long ss_i, ss_k;
-  const double *X;
+  const T *X;
   long long xs_k, xs_j;
-  double *Y;
+  T *Y;
   long long ys_i, ys_j;
-  double alpha, beta;
+  T alpha, beta;
   int kc, nchunks, jblocks;
-  double *partial;     // [nchunks][R][N] when nchunks > 1
+  T *partial;     // [nchunks][R][N] when nchunks > 1
   unsigned *counters;  // one per column block, zero between launches: the CTA that finds nchunks - 1 adds the partial sums
 };
 
@@ -51,22 +52,22 @@ constexpr int MAX_COUNTERS = 4096;
 // registers one unit ahead (the global latency of the tile would otherwise sit between every two units: a CTA computes a
 // unit in a few hundred cycles) and stored into the other of two shared-memory buffers.  The faster index of the fetch
 // follows S's contiguous direction.
-template <int R, int KC>
+template <typename T, int R, int KC>
 struct STile {
   static constexpr int PER = (R * KC + THREADS - 1) / THREADS;
-  double v[PER];
-  __device__ __forceinline__ void fetch(const Params &p, int k0, int k_end) {
+  T v[PER];
+  __device__ __forceinline__ void fetch(const Params<T> &p, int k0, int k_end) {
 #pragma unroll
     for (int t = 0; t < PER; t++) {
       const int idx = threadIdx.x + t * THREADS;
       int i, kk;
       if (p.ss_k == 1) { kk = idx % KC; i = idx / KC; } else { i = idx % R; kk = idx / R; }
-      v[t] = 0.0;
+      v[t] = T(0);
       if (idx < R * KC && i < p.r && k0 + kk < k_end) v[t] = __ldg(p.S + i * p.ss_i + (long long)(k0 + kk) * p.ss_k);
     }
   }
   template <bool K_MAJOR /* sm[kk][i] (true) or sm[i][kk] */>
-  __device__ __forceinline__ void store(const Params &p, double *sm) const {
+  __device__ __forceinline__ void store(const Params<T> &p, T *sm) const {
 #pragma unroll
     for (int t = 0; t < PER; t++) {
       const int idx = threadIdx.x + t * THREADS;
@@ -77,22 +78,23 @@ struct STile {
   }
 };
 
-__device__ __forceinline__ void finish(const Params &p, int i, int j, double sum) {
-  double *y = p.Y + i * p.ys_i + j * p.ys_j;
-  double v = p.alpha * sum;
-  if (p.beta != 0.0) v += p.beta * *y;
+template <typename T>
+__device__ __forceinline__ void finish(const Params<T> &p, int i, int j, T sum) {
+  T *y = p.Y + i * p.ys_i + j * p.ys_j;
+  T v = p.alpha * sum;
+  if (p.beta != T(0)) v += p.beta * *y;
   *y = v;
 }
 
 // sum of output (i, j) over the chunks, in chunk order; loads in batches of 8 (one memory latency per batch, not per chunk)
-template <int R>
-__device__ __forceinline__ double ordered_sum(const Params &p, int i, int j) {
-  const double *src = p.partial + (size_t)i * p.N + j;
+template <typename T, int R>
+__device__ __forceinline__ T ordered_sum(const Params<T> &p, int i, int j) {
+  const T *src = p.partial + (size_t)i * p.N + j;
   const size_t step = (size_t)R * p.N;
-  double sum = 0.0;
+  T sum = T(0);
   int c = 0;
   for (; c + 8 <= p.nchunks; c += 8) {
-    double v[8];
+    T v[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (size_t)(c + u) * step);
 #pragma unroll
@@ -104,7 +106,8 @@ __device__ __forceinline__ double ordered_sum(const Params &p, int i, int j) {
 
 // After a CTA has stored its partial sums: the last of a column block's nchunks CTAs to arrive adds them up — in chunk
 // order whoever it is, so the result does not depend on the arrival order — and resets the counter for the next launch.
-__device__ __forceinline__ bool last_of_column_block(const Params &p, int jb) {
+template <typename T>
+__device__ __forceinline__ bool last_of_column_block(const Params<T> &p, int jb) {
   __shared__ unsigned arrived;
   if (!p.counters) return false;  // separate reduction kernel (more column blocks than counters)
   __threadfence();   // this thread's partial sums before the counter
@@ -120,17 +123,17 @@ __device__ __forceinline__ bool last_of_column_block(const Params &p, int jb) {
 }
 
 // ---- X contiguous along N ---------------------------------------------------------------------------------------
-template <int R, int KC, bool PIPE>
-__global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
-  __shared__ __align__(16) double sm[PIPE ? 2 : 1][KC * R];
+template <typename T, int R, int KC, bool PIPE>
+__global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params<T> p) {
+  __shared__ __align__(16) T sm[PIPE ? 2 : 1][KC * R];
   const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
   const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
   const int j = jb * THREADS + threadIdx.x;
   const bool active = j < p.N;
-  double acc[R];
+  T acc[R];
 #pragma unroll
-  for (int i = 0; i < R; i++) acc[i] = 0.0;
-  STile<R, KC> next;
+  for (int i = 0; i < R; i++) acc[i] = T(0);
+  STile<T, R, KC> next;
   if (PIPE) next.fetch(p, k_begin, k_end);
   int buf = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += KC, buf ^= PIPE ? 1 : 0) {
@@ -146,12 +149,12 @@ __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
       __syncthreads();
     }
     if (!active) continue;
-    const double *xp = p.X + (long long)k0 * p.xs_k + j;
+    const T *xp = p.X + (long long)k0 * p.xs_k + j;
     constexpr int U = R <= 2 ? 16 : 8;  // loads in flight per thread: a GEMV lives on memory-level parallelism
     for (int kk = 0; kk < kc; kk += U) {
-      double x[U];
+      T x[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) x[u] = (kk + u < kc) ? __ldg(xp + (long long)(kk + u) * p.xs_k) : 0.0;
+      for (int u = 0; u < U; u++) x[u] = (kk + u < kc) ? __ldg(xp + (long long)(kk + u) * p.xs_k) : T(0);
 #pragma unroll
       for (int u = 0; u < U; u++)
 #pragma unroll
@@ -173,27 +176,27 @@ __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params p) {
   if (!last_of_column_block(p, jb) || !active) return;
 #pragma unroll
   for (int i = 0; i < R; i++)
-    if (i < p.r) finish(p, i, j, ordered_sum<R>(p, i, j));
+    if (i < p.r) finish(p, i, j, ordered_sum<T, R>(p, i, j));
 }
 
 // ---- X contiguous along K ---------------------------------------------------------------------------------------
-template <int R, int KC, int JW, bool PIPE>
-__global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
-  __shared__ __align__(16) double sm[PIPE ? 2 : 1][R * KC];
+template <typename T, int R, int KC, int JW, bool PIPE>
+__global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params<T> p) {
+  __shared__ __align__(16) T sm[PIPE ? 2 : 1][R * KC];
   const int jb = blockIdx.x % p.jblocks, chunk = blockIdx.x / p.jblocks;
   const int k_begin = chunk * p.kc, k_end = min(k_begin + p.kc, p.K);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int j0 = (jb * (THREADS / 32) + warp) * JW;
   const bool active = j0 < p.N;
-  double acc[JW][R];
+  T acc[JW][R];
 #pragma unroll
   for (int jj = 0; jj < JW; jj++)
 #pragma unroll
-    for (int i = 0; i < R; i++) acc[jj][i] = 0.0;
-  const double *xp[JW];
+    for (int i = 0; i < R; i++) acc[jj][i] = T(0);
+  const T *xp[JW];
 #pragma unroll
   for (int jj = 0; jj < JW; jj++) xp[jj] = p.X + (long long)min(j0 + jj, p.N - 1) * p.xs_j;  // clamped: never stored
-  STile<R, KC> next;
+  STile<T, R, KC> next;
   if (PIPE) next.fetch(p, k_begin, k_end);
   int buf = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += KC, buf ^= PIPE ? 1 : 0) {
@@ -212,12 +215,12 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
 #pragma unroll
     for (int t = 0; t < KC / 32; t++) {
       const int kk = lane + 32 * t;
-      double x[JW];
+      T x[JW];
 #pragma unroll
-      for (int jj = 0; jj < JW; jj++) x[jj] = kk < kc ? __ldg(xp[jj] + k0 + kk) : 0.0;
+      for (int jj = 0; jj < JW; jj++) x[jj] = kk < kc ? __ldg(xp[jj] + k0 + kk) : T(0);
 #pragma unroll
       for (int i = 0; i < R; i++) {
-        const double sv = sm[buf][i * KC + kk];
+        const T sv = sm[buf][i * KC + kk];
 #pragma unroll
         for (int jj = 0; jj < JW; jj++) acc[jj][i] = fma(sv, x[jj], acc[jj][i]);
       }
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
     for (int jj = 0; jj < JW; jj++)
 #pragma unroll
       for (int i = 0; i < R; i++) {
-        double v = acc[jj][i];
+        T v = acc[jj][i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         acc[jj][i] = v;
@@ -255,24 +258,25 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params p) {
   constexpr int COLS = (THREADS / 32) * JW;
   for (int o = threadIdx.x; o < COLS * R; o += THREADS) {
     const int i = o / COLS, j = jb * COLS + o % COLS;
-    if (i < p.r && j < p.N) finish(p, i, j, ordered_sum<R>(p, i, j));
+    if (i < p.r && j < p.N) finish(p, i, j, ordered_sum<T, R>(p, i, j));
   }
 }
 
 // partial sums -> Y, chunks added in order: the fallback when a launch has more column blocks than counters
-__global__ void __launch_bounds__(THREADS) skinny_reduce_kernel(const Params p, int R) {
+template <typename T>
+__global__ void __launch_bounds__(THREADS) skinny_reduce_kernel(const Params<T> p, int R) {
   const long long idx = (long long)blockIdx.x * THREADS + threadIdx.x;
   if (idx >= (long long)p.r * p.N) return;
   const int i = int(idx / p.N), j = int(idx % p.N);
-  const double *src = p.partial + (size_t)i * p.N + j;
+  const T *src = p.partial + (size_t)i * p.N + j;
   const size_t step = (size_t)R * p.N;
-  double sum = 0.0;
+  T sum = T(0);
   for (int c = 0; c < p.nchunks; c++) sum += __ldcg(src + (size_t)c * step);
   finish(p, i, j, sum);
 }
 
-template <int R>
-static int run(rtat_b200_context *h, Params p) {
+template <typename T, int R>
+static int run(rtat_b200_context *h, Params<T> p) {
   const bool xj = p.xs_j == 1;
   // k per shared-memory S tile (R x KC doubles): short tiles give the N-contiguous GEMVs more CTAs (1 x 8192 x 2048:
   // 42 -> 31 us); the K-contiguous kernel folds its sums with shuffles once per chunk and wants chunks of 512 k or more
@@ -292,10 +296,10 @@ static int run(rtat_b200_context *h, Params p) {
   p.nchunks = (p.K + p.kc - 1) / p.kc;
   bool fused = true;
   if (p.nchunks > 1) {
-    const size_t bytes = sizeof(double) * (size_t)p.nchunks * R * p.N;
+    const size_t bytes = sizeof(T) * (size_t)p.nchunks * R * p.N;
     if (bytes > (size_t(256) << 20)) return RTAT_B200_STATUS_NOT_SUPPORTED;
     if (int st = ensure_arena(h, bytes)) return st;
-    p.partial = static_cast<double *>(h->arena);
+    p.partial = static_cast<T *>(h->arena);
     fused = p.jblocks <= MAX_COUNTERS && opt(h, "dgemm.skinny_fused", 1) != 0;
     if (fused && !h->skinny_counters) {
       if (cudaMalloc(&h->skinny_counters, MAX_COUNTERS * sizeof(unsigned)) != cudaSuccess ||
@@ -308,7 +312,7 @@ static int run(rtat_b200_context *h, Params p) {
   }
   const long long grid = (long long)p.jblocks * p.nchunks;
   if (grid > 0x7fffffffLL) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  const Params &pk = p;
+  const Params<T> &pk = p;
   // S tile fetched one unit ahead into a second buffer (PIPE) or in place between two barriers: option dgemm.skinny_pipe
   // (0 = choose, 1 / 2 = on / off)
   const int units_per_cta = p.kc / KC;
@@ -317,35 +321,49 @@ static int run(rtat_b200_context *h, Params p) {
   // 8192 x 4 x 2048 44 / 72; K-contiguous X 1 x 8192 x 2048 58 / 37, 4 x 8192 x 2048 51 / 54, 32768 x 2 x 32768 1389 / 1763
   if (pipe == 0) pipe = (xj || R >= 4 || units_per_cta >= 32) ? 1 : 2;
   if (xj) {
-    if (pipe == 1) skinny_xj_kernel<R, KCJ, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
-    else skinny_xj_kernel<R, KCJ, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    if (pipe == 1) skinny_xj_kernel<T, R, KCJ, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    else skinny_xj_kernel<T, R, KCJ, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
   } else {
-    if (pipe == 1) skinny_xk_kernel<R, KCK, JW, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
-    else skinny_xk_kernel<R, KCK, JW, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    if (pipe == 1) skinny_xk_kernel<T, R, KCK, JW, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
+    else skinny_xk_kernel<T, R, KCK, JW, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
   }
-  int st = check_launch(h, xj ? "dgemm_skinny_fma_xn" : "dgemm_skinny_fma_xk");
+  constexpr bool DBL = sizeof(T) == 8;
+  int st = check_launch(h, DBL ? (xj ? "dgemm_skinny_fma_xn" : "dgemm_skinny_fma_xk") : (xj ? "sgemm_skinny_fma_xn" : "sgemm_skinny_fma_xk"));
   if (st || p.nchunks == 1 || fused) return st;
   const long long outs = (long long)p.r * p.N;
-  skinny_reduce_kernel<<<(unsigned)((outs + THREADS - 1) / THREADS), THREADS, 0, h->stream>>>(p, R);
-  return check_launch(h, xj ? "dgemm_skinny_fma_xn+reduce" : "dgemm_skinny_fma_xk+reduce");
+  skinny_reduce_kernel<T><<<(unsigned)((outs + THREADS - 1) / THREADS), THREADS, 0, h->stream>>>(p, R);
+  return check_launch(h, DBL ? (xj ? "dgemm_skinny_fma_xn+reduce" : "dgemm_skinny_fma_xk+reduce")
+                             : (xj ? "sgemm_skinny_fma_xn+reduce" : "sgemm_skinny_fma_xk+reduce"));
 }
 
 }  // namespace skinny
 
 // Y (r x N) = alpha S X + beta Y with element strides; NOT_SUPPORTED when the strip is not skinny or X has no unit stride.
-int dgemm_skinny(rtat_b200_context *h, int r, int N, int K, double alpha, const double *S, long long ss_i, long long ss_k, const double *X,
-                 long long xs_k, long long xs_j, double beta, double *Y, long long ys_i, long long ys_j) {
-  // Wider strips are FMA-bound here (r = 8: 6 TFLOP/s, slower than the tile kernel's padded DMMAs): measured break-even r = 4
+template <typename T>
+static int skinny_entry(rtat_b200_context *h, int r, int N, int K, T alpha, const T *S, long long ss_i, long long ss_k, const T *X, long long xs_k,
+                        long long xs_j, T beta, T *Y, long long ys_i, long long ys_j) {
+  // Wider strips are FMA-bound here (FP64, r = 8: 6 TFLOP/s, slower than the tile kernel's padded DMMAs): measured break-even r = 4
   if (r < 1 || r > skinny::SKINNY_MAX_ROWS || N < 1 || K < 1 || (xs_k != 1 && xs_j != 1)) return RTAT_B200_STATUS_NOT_SUPPORTED;
-  skinny::Params p{};
+  skinny::Params<T> p{};
   p.r = r; p.N = N; p.K = K;
   p.S = S; p.ss_i = ss_i; p.ss_k = ss_k;
   p.X = X; p.xs_k = xs_k; p.xs_j = xs_j;
   p.Y = Y; p.ys_i = ys_i; p.ys_j = ys_j;
   p.alpha = alpha; p.beta = beta;
-  if (r == 1) return skinny::run<1>(h, p);
-  if (r == 2) return skinny::run<2>(h, p);
-  return skinny::run<4>(h, p);
+  if (r == 1) return skinny::run<T, 1>(h, p);
+  if (r == 2) return skinny::run<T, 2>(h, p);
+  return skinny::run<T, 4>(h, p);
+}
+
+int dgemm_skinny(rtat_b200_context *h, int r, int N, int K, double alpha, const double *S, long long ss_i, long long ss_k, const double *X,
+                 long long xs_k, long long xs_j, double beta, double *Y, long long ys_i, long long ys_j) {
+  return skinny_entry<double>(h, r, N, K, alpha, S, ss_i, ss_k, X, xs_k, xs_j, beta, Y, ys_i, ys_j);
+}
+
+// FP32: plain FP32 FMAs (the arithmetic of the reference's cublasSgemm in its default math mode)
+int sgemm_skinny(rtat_b200_context *h, int r, int N, int K, float alpha, const float *S, long long ss_i, long long ss_k, const float *X,
+                 long long xs_k, long long xs_j, float beta, float *Y, long long ys_i, long long ys_j) {
+  return skinny_entry<float>(h, r, N, K, alpha, S, ss_i, ss_k, X, xs_k, xs_j, beta, Y, ys_i, ys_j);
 }
 
 }  // namespace rtat_b200

@@ -500,35 +500,39 @@ def test_dgemm_thin_remainders_are_peeled_into_a_second_launch(oracle, handle, t
         handle.set_option("dgemm.skinny", 1)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("ta,tb", OPS)
-def test_dgemm_gemv_shaped_calls_take_the_skinny_kernel(oracle, handle, ta, tb):
-    """C at most 4 rows or columns wide (and the other extent >= 256): the skinny kernel, both orientations of the large
-    operand, K cut into chunks whose partial sums are added in order (several chunks / a single one), alpha / beta, odd
-    leading dimensions, element-aligned bases; bit-identical when repeated."""
+def test_gemv_shaped_calls_take_the_skinny_kernel(oracle, handle, ta, tb, dtype):
+    """C at most 4 rows or columns wide (and the other extent >= 256): the skinny FMA kernel (FP64, and FP32 with plain FP32
+    arithmetic), both orientations of the large operand, K cut into chunks whose partial sums are added in order (several
+    chunks / a single one), alpha / beta, odd leading dimensions, element-aligned bases; bit-identical when repeated."""
+    dbl = dtype == np.float64
+    prefix = ("d" if dbl else "s") + "gemm_skinny_fma"
     for (m, n, k, beta) in [(1, 3001, 2049, 0.0), (3, 700, 130, -0.5), (4, 260, 1000, 1.0), (2, 5000, 64, 0.0),
                             (3001, 1, 2049, 0.0), (700, 4, 130, 0.5), (300, 2, 4097, 0.0), (5000, 3, 17, 1.0)]:
-        _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, 1.5, beta, 9700 + m + n, ldc_pad=3, nan_c=(beta == 0.0))
-        assert handle.last_kernel().startswith("dgemm_skinny_fma"), handle.last_kernel()
-        _gemm_case(oracle, handle, np.float64, ta, tb, m, n, k, -1.0, beta, 9800 + m + n, lda_pad=1, ldb_pad=3, ldc_pad=1, offset=1)
-        assert handle.last_kernel().startswith("dgemm_skinny_fma"), handle.last_kernel()
+        _gemm_case(oracle, handle, dtype, ta, tb, m, n, k, 1.5, beta, 9700 + m + n, ldc_pad=3, nan_c=(beta == 0.0))
+        assert handle.last_kernel().startswith(prefix), handle.last_kernel()
+        _gemm_case(oracle, handle, dtype, ta, tb, m, n, k, -1.0, beta, 9800 + m + n, lda_pad=1, ldb_pad=3, ldc_pad=1, offset=1)
+        assert handle.last_kernel().startswith(prefix), handle.last_kernel()
     handle.set_option("dgemm.skinny", 0)
     try:
-        _gemm_case(oracle, handle, np.float64, ta, tb, 1, 3001, 200, 1.5, 0.0, 9790)
+        _gemm_case(oracle, handle, dtype, ta, tb, 1, 3001, 200, 1.5, 0.0, 9790)
         assert "skinny" not in handle.last_kernel()
     finally:
         handle.set_option("dgemm.skinny", 1)
     m, n, k = (2, 4100, 3000)
     ar, ac = (k, m) if ta else (m, k)
     br, bc = (n, k) if tb else (k, n)
+    tdt = torch.float64 if dbl else torch.float32
     g = torch.Generator(device="cuda").manual_seed(5)
-    A = torch.rand(ar * ac, dtype=torch.float64, device="cuda", generator=g) - 0.5
-    B = torch.rand(br * bc, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    A = torch.rand(ar * ac, dtype=tdt, device="cuda", generator=g) - 0.5
+    B = torch.rand(br * bc, dtype=tdt, device="cuda", generator=g) - 0.5
     outs = []
     for _ in range(20):
-        Cm = torch.zeros(m * n, dtype=torch.float64, device="cuda")
-        handle.gemm(True, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m)
+        Cm = torch.zeros(m * n, dtype=tdt, device="cuda")
+        handle.gemm(dbl, ta, tb, m, n, k, 1.0, A, ar, B, br, 0.0, Cm, m)
         outs.append(Cm)
-    assert handle.last_kernel().startswith("dgemm_skinny_fma")
+    assert handle.last_kernel().startswith(prefix)
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 

@@ -140,7 +140,13 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *     dgemm.skinny_pipe [0]     1 / 2: S tiles of the skinny kernel fetched one tile ahead always / never (0 = by shape)
  *     dgemm.group [8]           tile rows the grouped raster of the persistent DGEMM sweeps across n together
  *     dgemm.ktail [1]           0: the last k-tile of a k that is not a multiple of 16 runs all four DMMA steps
- *     dgemm.streamk [1]         0: data-parallel schedule only
+ *     dgemm.streamk [1]         0: data-parallel schedule only.  Stream-K note: the CTA that owns a tile's first k-tile
+ *                               waits for partial tiles from higher-numbered CTAs of the same launch.  CTAs are issued in
+ *                               order and the lower ones can always finish, so a launch that is only partly resident
+ *                               (other work holding SMs) still completes; the wait is bounded all the same (20 s, then
+ *                               the kernel traps and the call surfaces a CUDA error instead of hanging the GPU).  Callers
+ *                               that run several handles on concurrent streams and want no such dependency at all set
+ *                               this option to 0.
  *     dgemm.tma3d [1]           0: eight 2-D TMA boxes per M/N-contiguous operand stage instead of one 3-D box
  *     dgemm.peel [1]            0: keep remainders of 1..16 rows / columns in the 128x128 launch instead of a second
  *                               launch on 64x64 tiles

@@ -24,11 +24,13 @@ for (rows, cols, ldo) in [(4097, 2049, 4128), (3001, 2049, 3008), (4097, 3001, 4
     out = torch.empty(ldo * cols, dtype=torch.float64, device="cuda")
     fn = lambda: h.geam(True, 0, 0, rows, cols, 1.0, A, rows, 0.0, out, ldo, out, ldo)
     nbytes = 2.0 * rows * cols * 8
-    for ev in (0, 1):
-        h.set_option("geam.even_chunks", ev)
+    for ev in (0, 1, 2):
+        h.set_option("geam.even_chunks", min(ev, 1))
+        h.set_option("geam.persistent", 1 if ev == 2 else 0)
         for _ in range(3):
             fn()
         cold, warm = timed(fn, 30, True), timed(fn, 30, False)
         ok = bool(torch.equal(out.view(cols, ldo)[:, :rows], A.view(cols, rows)))
-        print(f"{rows}x{cols} -> ld {ldo}  even_chunks {ev} {h.last_kernel():20s} cold {cold*1e3:7.2f} us {nbytes/cold*1e-6:7.0f} GB/s   warm {warm*1e3:7.2f} us {nbytes/warm*1e-6:7.0f} GB/s  exact {ok}", flush=True)
+        print(f"{rows}x{cols} -> ld {ldo}  even_chunks/persistent {ev} {h.last_kernel():20s} cold {cold*1e3:7.2f} us {nbytes/cold*1e-6:7.0f} GB/s   warm {warm*1e3:7.2f} us {nbytes/warm*1e-6:7.0f} GB/s  exact {ok}", flush=True)
     h.set_option("geam.even_chunks", 1)
+    h.set_option("geam.persistent", 0)

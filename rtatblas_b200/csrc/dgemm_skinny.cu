@@ -149,16 +149,31 @@ __global__ void __launch_bounds__(THREADS) skinny_xj_kernel(const Params<T> p) {
       __syncthreads();
     }
     if (!active) continue;
+    // X in batches of U, the loads of batch b + 1 issued before the FMAs of batch b: written as a straight batch (loads, then
+    // FMAs) ptxas kept 3-5 loads in flight and stalled the first FMA on them (32 registers; SASS, r = 1); a GEMV lives on
+    // memory-level parallelism
     const T *xp = p.X + (long long)k0 * p.xs_k + j;
-    constexpr int U = R <= 2 ? 16 : 8;  // loads in flight per thread: a GEMV lives on memory-level parallelism
-    for (int kk = 0; kk < kc; kk += U) {
-      T x[U];
+    constexpr int U = 8, NB = KC / U;
+    static_assert(NB % 2 == 0, "batches are processed in pairs");
+    auto load = [&](T (&x)[U], int kk) {
 #pragma unroll
       for (int u = 0; u < U; u++) x[u] = (kk + u < kc) ? __ldg(xp + (long long)(kk + u) * p.xs_k) : T(0);
+    };
+    auto fmas = [&](const T (&x)[U], int kk) {
 #pragma unroll
       for (int u = 0; u < U; u++)
 #pragma unroll
         for (int i = 0; i < R; i++) acc[i] = fma(sm[buf][(kk + u) * R + i], x[u], acc[i]);  // rows of sm beyond kc are zero
+    };
+    T xa[U], xb[U];
+    load(xa, 0);
+#pragma unroll
+    for (int b = 0; b < NB; b += 2) {
+      if (b * U >= kc) break;
+      load(xb, (b + 1) * U);
+      fmas(xa, b * U);
+      if (b + 2 < NB) load(xa, (b + 2) * U);
+      fmas(xb, (b + 1) * U);
     }
   }
   if (p.nchunks == 1) {
@@ -196,6 +211,14 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params<T> p) {
   const T *xp[JW];
 #pragma unroll
   for (int jj = 0; jj < JW; jj++) xp[jj] = p.X + (long long)min(j0 + jj, p.N - 1) * p.xs_j;  // clamped: never stored
+  T xn[KC / 32][JW];
+  auto load_x = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < KC / 32; t++)
+#pragma unroll
+      for (int jj = 0; jj < JW; jj++) xn[t][jj] = (k0 + lane + 32 * t < k_end) ? __ldg(xp[jj] + k0 + lane + 32 * t) : T(0);
+  };
+  if (active) load_x(k_begin);
   STile<T, R, KC> next;
   if (PIPE) next.fetch(p, k_begin, k_end);
   int buf = 0;
@@ -212,17 +235,21 @@ __global__ void __launch_bounds__(THREADS) skinny_xk_kernel(const Params<T> p) {
       __syncthreads();
     }
     if (!active) continue;
+    // this unit's KC / 32 x JW elements of X were asked for one unit ago (xn); the next unit's go out before this one's FMAs
+    T xc[KC / 32][JW];
+#pragma unroll
+    for (int t = 0; t < KC / 32; t++)
+#pragma unroll
+      for (int jj = 0; jj < JW; jj++) xc[t][jj] = xn[t][jj];
+    if (k0 + KC < k_end) load_x(k0 + KC);
 #pragma unroll
     for (int t = 0; t < KC / 32; t++) {
       const int kk = lane + 32 * t;
-      T x[JW];
-#pragma unroll
-      for (int jj = 0; jj < JW; jj++) x[jj] = kk < kc ? __ldg(xp[jj] + k0 + kk) : T(0);
 #pragma unroll
       for (int i = 0; i < R; i++) {
-        const T sv = sm[buf][i * KC + kk];
+        const T sv = sm[buf][i * KC + kk];  // zero beyond kc, and so is xc
 #pragma unroll
-        for (int jj = 0; jj < JW; jj++) acc[jj][i] = fma(sv, x[jj], acc[jj][i]);
+        for (int jj = 0; jj < JW; jj++) acc[jj][i] = fma(sv, xc[t][jj], acc[jj][i]);
       }
     }
   }
@@ -315,11 +342,11 @@ static int run(rtat_b200_context *h, Params<T> p) {
   const Params<T> &pk = p;
   // S tile fetched one unit ahead into a second buffer (PIPE) or in place between two barriers: option dgemm.skinny_pipe
   // (0 = choose, 1 / 2 = on / off)
-  const int units_per_cta = p.kc / KC;
   int pipe = opt(h, "dgemm.skinny_pipe", 0);
-  // measured (probe/perf_gemv_vs_cublas.py, us, on / off): N-contiguous X 1 x 8192 x 4096 54.5 / 53.5, 4 x 8192 x 4096 79 / 136,
-  // 8192 x 4 x 2048 44 / 72; K-contiguous X 1 x 8192 x 2048 58 / 37, 4 x 8192 x 2048 51 / 54, 32768 x 2 x 32768 1389 / 1763
-  if (pipe == 0) pipe = (xj || R >= 4 || units_per_cta >= 32) ? 1 : 2;
+  // measured with the X loads pipelined (probe/perf_gemv_vs_cublas.py, us, on / off): N-contiguous X 1 x 8192 x 4096 45.2 / 47.2,
+  // 32768 x 1 x 32768 1170 / 1196; K-contiguous X 4 x 8192 x 2048 37.0 / 41.4, 1 x 8192 x 2048 26.8 / 26.8, 32768 x 2 x 32768
+  // 1374 / 1281
+  if (pipe == 0) pipe = (xj || R >= 4) ? 1 : 2;
   if (xj) {
     if (pipe == 1) skinny_xj_kernel<T, R, KCJ, true><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);
     else skinny_xj_kernel<T, R, KCJ, false><<<(unsigned)grid, THREADS, 0, h->stream>>>(pk);

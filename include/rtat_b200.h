@@ -153,7 +153,8 @@ int rtat_b200_fill_uniform_s(rtat_b200_handle_t handle, float *x, size_t n, uint
  *     dgemm.prefetch_c [1]      0: beta != 0 without the L2 prefetch of the C tile at the start of its main loop
  *     dgemm.l2_hints [0]        1: evict_last / evict_first on the A / B loads (measured: more DRAM traffic)
  *     dgemm.force_unaligned [0] 1: cp.async producers even when TMA could address the operands
- *     sgemm.presplit [1]        0: split op(B) into big / small TF32 parts per tile instead of once per call
+ *     sgemm.presplit [1]        0: split op(B) into big / small TF32 parts per tile instead of once per call; 1: once per
+ *                               call from 768^3 multiply-adds on (or when TMA cannot address B as stored); 2: always
  *     sgemm.pair [1]            0: single-CTA tcgen05 kernel instead of CTA pairs (cta_group::2)
  *     sgemm.pad_a [1]           0: an op(A) TMA cannot address goes to the FP32 SIMT kernel instead of an aligned copy
  *     geam.transpose [0]        transposing geam: 1 = TMA pipeline, 2 = register-blocked kernel (the default choice),

@@ -828,8 +828,12 @@ static int launch_pair(rtat_b200_context *h, const Params &p, const CUtensorMap 
 // by at least two M-tiles; B then needs no alignment at all (the pre-pass reads any ldb).
 constexpr size_t PRESPLIT_LIMIT = size_t(4) << 30;  // 16384^2 floats of B -> 2 GB of arena; beyond that B is split per tile in shared memory
 
-static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k) {
+// b_addressable: TMA can read B as stored, so the pre-split is a choice.  It is not made for small products, where the extra
+// launch costs more than splitting op(B) again in every M-tile (256^3: 18.5 -> 14.5 us, 512^3: 22.6 -> 20.1, 768^3: 26.7 ->
+// 24.7; from 1024^3 or k = 4096 on the pre-split is level or ahead: 512 x 512 x 4096 73.9 against 89.9 us; probe/perf_sgemm_small2.py)
+static bool presplit_wanted(const rtat_b200_context *h, int m, int n, int k, bool b_addressable) {
   if (opt(h, "sgemm.presplit", 1) == 0) return false;
+  if (b_addressable && opt(h, "sgemm.presplit", 1) != 2 && (double)m * n * k <= 768.0 * 768.0 * 768.0) return false;
   // either stored orientation of B: rows rounded up to 4 floats
   const size_t bytes_n = 2 * sizeof(float) * ((size_t)(k + 3) / 4 * 4) * (size_t)n;  // stored k x n
   const size_t bytes_t = 2 * sizeof(float) * ((size_t)(n + 3) / 4 * 4) * (size_t)k;  // stored n x k
@@ -852,7 +856,7 @@ bool sgemm_tcgen05_supported(const rtat_b200_context *h, int transa, int, int m,
   auto ok = [](const void *ptr, int ld) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && ld % 4 == 0; };
   if (!(m > 0 && n > 0 && k > 0)) return false;
   if (!ok(A, lda) && !pad_a_wanted(h, transa == RTAT_B200_OP_T, m, n, k)) return false;
-  return ok(B, ldb) || presplit_wanted(h, m, n, k);
+  return ok(B, ldb) || presplit_wanted(h, m, n, k, false);
 }
 
 int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, int k, float alpha, const float *A, int lda, const float *B,
@@ -896,7 +900,8 @@ int sgemm_tcgen05(rtat_b200_context *h, int transa, int transb, int m, int n, in
     lda = ldp;
     padded_a = true;
   }
-  const bool presplit = presplit_wanted(h, m, n, k);
+  // (SYRK keeps the pre-split, and with it the CTA pairs, at every size: its timings were taken that way)
+  const bool presplit = presplit_wanted(h, m, n, k, !tri && reinterpret_cast<uintptr_t>(B) % 16 == 0 && ldb % 4 == 0);
   const float *Bbig = B, *Bsmall = B;
   int ldb_eff = ldb;
   if (presplit) {

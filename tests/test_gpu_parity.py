@@ -618,10 +618,12 @@ def test_gemm_host_entry_k_panel_pipeline(handle, ta, tb):
 # SGEMM on tcgen05 (3xTF32): forced with sgemm.variant = 2; needs 16 B aligned operands, ld % 4 == 0
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ta,tb", OPS)
-@pytest.mark.parametrize("presplit", [1, 0])
+@pytest.mark.parametrize("presplit", [2, 1, 0])
 def test_sgemm_tcgen05_3xtf32(oracle, handle, ta, tb, presplit):
     handle.set_option("sgemm.variant", 2)
-    handle.set_option("sgemm.presplit", presplit)  # 1: op(B) split once into the arena; 0: split per tile in shared memory
+    # 2: op(B) split once into the arena whatever the size; 1 (default): only from 768^3 multiply-adds on, or when TMA cannot
+    # address B as stored; 0: split per tile in shared memory
+    handle.set_option("sgemm.presplit", presplit)
     try:
         for (m, n, k) in [(128, 128, 32), (128, 128, 64), (256, 128, 96), (260, 132, 100), (64, 48, 40), (1, 1, 1), (513, 257, 33), (1024, 384, 520)]:
             # leading dimensions rounded up to a multiple of 4 floats (what TMA can address)
@@ -632,6 +634,8 @@ def test_sgemm_tcgen05_3xtf32(oracle, handle, ta, tb, presplit):
             assert handle.last_kernel().startswith("sgemm_tcgen05"), handle.last_kernel()
             _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, -1.5, 0.75, 800 + m + k, lda_pad=pad_a + 4, ldb_pad=pad_b + 8, ldc_pad=3)
             _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.0, 0.0, 900 + m + k, lda_pad=pad_a, ldb_pad=pad_b, nan_c=True)
+            if presplit == 2 and m > 128:
+                assert handle.last_kernel().endswith("presplitB"), handle.last_kernel()
             if presplit and m > 128:  # the pre-pass reads any ldb / alignment of B
                 _gemm_case(oracle, handle, np.float32, ta, tb, m, n, k, 1.0, 0.0, 950 + m + k, lda_pad=pad_a, ldb_pad=pad_b + 1)
                 assert handle.last_kernel().endswith("presplitB"), handle.last_kernel()
